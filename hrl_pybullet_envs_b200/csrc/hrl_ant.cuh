@@ -1,0 +1,550 @@
+// hrl_ant.cuh - one Bullet-style internal sub-step of the Ant, 4 lanes per env (one lane per leg).
+//
+// What this replaces: scene.global_step() -> p.stepSimulation() for the Ant multibody
+// (reference call site envs/gather/ant_gather_env.py:78; arithmetic in pybullet, restated in
+// oracle/hrl_oracle.c in a different formulation).
+//
+// Formulation (DESIGN.md "Kernel 1"): world-frame projected Newton-Euler.  The mass matrix of
+// the tree (6 base dofs + 4 legs x 2 hinges) is block-arrow: M = [[Mbb, G],[G^T, blkdiag(Mll_k)]].
+// Lane k eliminates its own leg (2x2 inverse), contributes its articulated inertia to the base
+// Schur complement S (21 unique entries, summed with two xor-shuffles), every lane then holds
+// S^-1 = L^-T L^-1 in registers.  A constraint row only touches the base and ONE leg, so the
+// row response M^-1 J^T is evaluated by the owning lane alone; the projected Gauss-Seidel sweep
+// keeps the base velocity delta replicated in all 4 lanes and the leg part private to its lane.
+#pragma once
+#include "hrl_math.cuh"
+#include "../../include/hrl_b200.h"
+
+#ifndef HRL_MAXC
+#define HRL_MAXC 4  // contacts kept per lane (= per contact group, oracle MAX_CONTACT_PER_GROUP)
+#endif
+#define HRL_NSLOT (2 + 3 * HRL_MAXC)
+// row fields in shared memory: [slot][field][lane]
+enum { RF_JB = 0, RF_JL = 6, RF_WB = 8, RF_Y = 14, RF_DINV = 16, RF_RHS = 17, RF_LAM = 18, RF_N = 19 };
+// contact candidates: [c][field][lane]: P-O (3), n (3), dist, body
+#define HRL_CAND_F 8
+#define HRL_SMEM_FLOATS_PER_WARP ((HRL_NSLOT * RF_N + HRL_MAXC * HRL_CAND_F) * 32)
+
+struct AntLane {
+  // replicated in the 4 lanes of an env
+  V3 O;                  // torso origin
+  float qx, qy, qz, qw;  // torso orientation
+  V3 v, w;               // world-frame linear (of O) / angular velocity
+  // private to the lane (leg k)
+  float q1, q2, qd1, qd2;  // hip_k, ankle_k
+};
+
+struct LegConst {
+  float sx, sy;    // ant.xml:15,26,37,48 leg direction signs
+  float axl, ayl;  // ankle axis in aux coords (ant.xml:21,32,43,54), normalised
+  float lo2, hi2;  // ankle limits
+};
+__device__ __forceinline__ LegConst leg_const(int k) {
+  LegConst c;
+  c.sx = (k == 0 || k == 3) ? 1.f : -1.f;
+  c.sy = (k < 2) ? 1.f : -1.f;
+  c.axl = (k == 0 || k == 2) ? -ant::IS2 : ant::IS2;
+  c.ayl = ant::IS2;
+  if (k == 0 || k == 3) { c.lo2 = ant::ANK_LO; c.hi2 = ant::ANK_HI; }
+  else { c.lo2 = -ant::ANK_HI; c.hi2 = -ant::ANK_LO; }
+  return c;
+}
+
+// leg geometry in world axes, relative to the torso origin
+struct LegKin {
+  V3 ex, ey, ez;  // torso frame axes
+  V3 rh;          // hip point - O
+  V3 r1;          // aux COM - hip   (ankle - hip = 2 r1)
+  V3 a2;          // ankle axis (hip axis a1 = ez)
+  V3 r2;          // foot COM - ankle (tip - ankle = 2 r2)
+  V3 zf;          // foot frame z axis
+};
+
+__device__ __forceinline__ LegKin leg_fk(const AntLane& s, const LegConst& c) {
+  LegKin K;
+  float x = s.qx, y = s.qy, z = s.qz, w = s.qw;
+  K.ex = mk(1.f - 2.f * (y * y + z * z), 2.f * (x * y + z * w), 2.f * (x * z - y * w));
+  K.ey = mk(2.f * (x * y - z * w), 1.f - 2.f * (x * x + z * z), 2.f * (y * z + x * w));
+  K.ez = mk(2.f * (x * z + y * w), 2.f * (y * z - x * w), 1.f - 2.f * (x * x + y * y));
+  V3 d0 = c.sx * K.ex + c.sy * K.ey;
+  K.rh = 0.2f * d0;
+  float s1, c1, s2, c2;
+  sincosf(s.q1, &s1, &c1);
+  sincosf(s.q2, &s2, &c2);
+  V3 auxx = c1 * K.ex + s1 * K.ey, auxy = c1 * K.ey - s1 * K.ex;
+  V3 d1 = c.sx * auxx + c.sy * auxy;
+  K.r1 = 0.1f * d1;
+  K.a2 = c.axl * auxx + c.ayl * auxy;
+  float wsgn = c.axl * c.sy - c.ayl * c.sx;      // a2 x d1 = wsgn * ez
+  V3 b = c.ayl * auxx - c.axl * auxy;            // a2 x ez
+  V3 d2 = c2 * d1 + (s2 * wsgn) * K.ez;          // Rodrigues, a2 _|_ d1
+  K.zf = c2 * K.ez + s2 * b;                     // a2 _|_ ez
+  K.r2 = 0.2f * d2;
+  return K;
+}
+
+// 6x6 symmetric index (i <= j)
+__host__ __device__ constexpr int sym6(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }
+
+struct LegDyn {
+  float mi11, mi12, mi22;  // Mll^-1
+  float G1[6], G2[6];      // base<-joint coupling columns [torque about O; force]
+  float K0[6], K1[6];      // (Mll^-1 G^T) rows = G Mll^-1 columns
+  float Li[21];            // L^-1 (lower, packed row-major: Li[i*(i+1)/2 + j], j <= i) of S = L L^T
+};
+
+// x = S^-1 b  via  L^-T (L^-1 b)
+__device__ __forceinline__ void sinv_mul(const float* __restrict__ Li, const float b[6], float x[6]) {
+  float t[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j <= i; j++) a = fmaf(Li[i * (i + 1) / 2 + j], b[j], a);
+    t[i] = a;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = i; j < 6; j++) a = fmaf(Li[j * (j + 1) / 2 + i], t[j], a);
+    x[i] = a;
+  }
+}
+
+__device__ __forceinline__ float clampf(float x, float lim) { return fminf(fmaxf(x, -lim), lim); }
+
+// Bullet btPlaneSpace1
+__device__ __forceinline__ void plane_space(V3 n, V3& p, V3& q) {
+  if (fabsf(n.z) > 0.7071067811865475244f) {
+    float a = n.y * n.y + n.z * n.z, k = rsqrtf(a);
+    p = mk(0.f, -n.z * k, n.y * k);
+    q = mk(a * k, -n.x * p.z, n.x * p.y);
+  } else {
+    float a = n.x * n.x + n.y * n.y, k = rsqrtf(a);
+    p = mk(-n.y * k, n.x * k, 0.f);
+    q = mk(-n.z * p.y, n.z * p.x, a * k);
+  }
+}
+
+struct SubstepParams {
+  float h, g, kl, ka, erp_c, erp_l, mu, max_imp, vmax, margin, gz;
+  float wx, wy;  // wall inner faces at +-wx, +-wy
+  int has_walls, has_box, iters;
+  float blo[3], bhi[3];
+};
+
+__device__ __forceinline__ SubstepParams make_params(const hrl_config& cfg) {
+  SubstepParams p;
+  p.h = cfg.dt / (float)cfg.substeps; p.g = cfg.gravity; p.kl = cfg.lin_damping; p.ka = cfg.ang_damping;
+  p.erp_c = cfg.contact_erp; p.erp_l = cfg.limit_erp; p.mu = cfg.friction; p.max_imp = cfg.limit_max_impulse;
+  p.vmax = cfg.max_coord_vel; p.margin = cfg.contact_margin; p.gz = cfg.ground_z;
+  p.wx = cfg.world_size[0] * 0.5f - 0.05f; p.wy = cfg.world_size[1] * 0.5f - 0.05f;
+  p.has_walls = cfg.has_walls; p.has_box = cfg.has_box; p.iters = cfg.solver_iters;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { p.blo[i] = cfg.box_lo[i]; p.bhi[i] = cfg.box_hi[i]; }
+  return p;
+}
+
+#define ROW(slot, f) rows[((slot) * RF_N + (f)) * 32 + lane]
+#define ROW_OF(slot, f, l) rows[((slot) * RF_N + (f)) * 32 + (l)]
+#define CAND(c, f) cands[((c) * HRL_CAND_F + (f)) * 32 + lane]
+
+// Finish one constraint row owned by this lane: reduced base Jacobian, response, diagonal, rhs.
+__device__ __forceinline__ void finish_row(float* __restrict__ rows, int lane, int slot, const LegDyn& D,
+                                           const float JB[6], float j1, float j2, const float ub[6], float u1,
+                                           float u2, float pen, float erp, float inv_h, bool positional) {
+  float y1 = D.mi11 * j1 + D.mi12 * j2, y2 = D.mi12 * j1 + D.mi22 * j2;
+  float Jt[6], W[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) Jt[i] = JB[i] - (D.G1[i] * y1 + D.G2[i] * y2);
+  sinv_mul(D.Li, Jt, W);
+  float diag = j1 * y1 + j2 * y2, rel = j1 * u1 + j2 * u2;
+#pragma unroll
+  for (int i = 0; i < 6; i++) { diag = fmaf(Jt[i], W[i], diag); rel = fmaf(JB[i], ub[i], rel); }
+  float dinv = 1.0f / diag;
+  float posErr = 0.f, velErr = -rel;
+  if (positional) {
+    if (pen > 0.f) velErr -= pen * inv_h;
+    else posErr = -pen * erp * inv_h;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) { ROW(slot, RF_JB + i) = Jt[i]; ROW(slot, RF_WB + i) = W[i]; }
+  ROW(slot, RF_JL) = j1; ROW(slot, RF_JL + 1) = j2;
+  ROW(slot, RF_Y) = y1; ROW(slot, RF_Y + 1) = y2;
+  ROW(slot, RF_DINV) = dinv;
+  ROW(slot, RF_RHS) = (posErr + velErr) * dinv;
+  ROW(slot, RF_LAM) = 0.f;
+}
+
+// One internal step of h = dt/substeps.  `rows`/`cands` point at this WARP's shared memory.
+// feet_ground: bit set when this leg's foot link (tip or ankle sphere) has a floor manifold at
+// the START of the sub-step (collision detection precedes the dynamics, like Bullet).
+__device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, const LegConst& lc, float tau1,
+                                            float tau2, float* __restrict__ rows, float* __restrict__ cands,
+                                            int lane, int k, int& feet_ground, int& stat_contacts, int& stat_limits) {
+  const LegKin K = leg_fk(s, lc);
+  const V3 a1 = K.ez, a2 = K.a2;
+  const V3 r_ac = K.rh + K.r1;           // aux COM - O
+  const V3 r_ank = K.rh + 2.f * K.r1;    // ankle - O
+  const V3 rf1 = 2.f * K.r1 + K.r2;      // foot COM - hip
+  const V3 r_fc = K.rh + rf1;            // foot COM - O
+  const V3 r_tip = r_ank + 2.f * K.r2;   // foot tip - O
+
+  // ---------------- contacts: spheres vs ground / walls / maze box (start-of-step poses) ----------
+  int nC = 0;
+  feet_ground = 0;
+  {
+    // candidate order inside the group: [torso sphere (lane 0)], tip (foot), ankle (aux), hip (torso)
+#pragma unroll
+    for (int si = 0; si < 4; si++) {
+      if (si == 0 && k != 0) continue;
+      V3 crel = si == 0 ? mk(0.f, 0.f, 0.f) : (si == 1 ? r_tip : (si == 2 ? r_ank : K.rh));
+      float r = si == 0 ? ant::R_TORSO : ant::R_CAPS;
+      float body = si == 0 ? 0.f : (si == 1 ? 2.f : (si == 2 ? 1.f : 0.f));
+      bool isfoot = (si == 1 || si == 2);
+      V3 c = s.O + crel;
+#pragma unroll
+      for (int surf = 0; surf < 6; surf++) {
+        V3 n; float dist;
+        if (surf == 0) { n = mk(0.f, 0.f, 1.f); dist = c.z - P.gz - r; }
+        else if (surf <= 4) {
+          if (!P.has_walls) continue;
+          if (surf == 1) { n = mk(-1.f, 0.f, 0.f); dist = P.wx - c.x - r; }
+          else if (surf == 2) { n = mk(1.f, 0.f, 0.f); dist = c.x + P.wx - r; }
+          else if (surf == 3) { n = mk(0.f, -1.f, 0.f); dist = P.wy - c.y - r; }
+          else { n = mk(0.f, 1.f, 0.f); dist = c.y + P.wy - r; }
+        } else {
+          if (!P.has_box) continue;
+          // sphere vs AABB
+          float cc[3] = {c.x, c.y, c.z}, qq[3];
+          bool inside = true;
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            float xx = cc[i];
+            if (xx < P.blo[i]) { xx = P.blo[i]; inside = false; }
+            if (xx > P.bhi[i]) { xx = P.bhi[i]; inside = false; }
+            qq[i] = xx;
+          }
+          if (!inside) {
+            V3 d = mk(cc[0] - qq[0], cc[1] - qq[1], cc[2] - qq[2]);
+            float len = norm(d);
+            n = (1.0f / len) * d; dist = len - r;
+          } else {
+            float best = 1e30f; int bi = 0; float bs = 1.f;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+              float dl = cc[i] - P.blo[i], dh = P.bhi[i] - cc[i];
+              if (dl < best) { best = dl; bi = i; bs = -1.f; }
+              if (dh < best) { best = dh; bi = i; bs = 1.f; }
+            }
+            n = mk(bi == 0 ? bs : 0.f, bi == 1 ? bs : 0.f, bi == 2 ? bs : 0.f);
+            dist = -best - r;
+          }
+        }
+        if (dist < P.margin) {
+          if (surf == 0 && isfoot) feet_ground = 1;
+          if (nC < HRL_MAXC) {
+            V3 Prel = crel - r * n;  // contact point on the robot, relative to O
+            CAND(nC, 0) = Prel.x; CAND(nC, 1) = Prel.y; CAND(nC, 2) = Prel.z;
+            CAND(nC, 3) = n.x; CAND(nC, 4) = n.y; CAND(nC, 5) = n.z;
+            CAND(nC, 6) = dist; CAND(nC, 7) = body;
+            nC++;
+          }
+        }
+      }
+    }
+  }
+
+  // ---------------- smooth dynamics: bias forces, leg elimination, base Schur complement ----------
+  LegDyn D;
+  float ub[6], u1, u2;  // generalized velocity after the unconstrained update
+  {
+    const V3 w = s.w, v = s.v;
+    const V3 w1 = w + s.qd1 * a1, w2 = w1 + s.qd2 * a2;
+    const V3 wxrh = cross(w, K.rh);
+    const V3 a_h = cross(w, wxrh);
+    const V3 al1 = s.qd1 * cross(w, a1);
+    const V3 w1xr1 = cross(w1, K.r1);
+    const V3 t1 = cross(al1, K.r1) + cross(w1, w1xr1);
+    const V3 a_ac = a_h + t1, a_ank = a_h + 2.f * t1;
+    const V3 al2 = al1 + s.qd2 * cross(w1, a2);
+    const V3 w2xr2 = cross(w2, K.r2);
+    const V3 a_fc = a_ank + cross(al2, K.r2) + cross(w2, w2xr2);
+    const V3 v_h = v + wxrh, v_ac = v_h + w1xr1, v_ank = v_h + 2.f * w1xr1, v_fc = v_ank + w2xr2;
+    const V3 v_lc = v + 0.5f * wxrh;
+    const V3 gz = mk(0.f, 0.f, P.g);
+    const V3 Iw1 = axisym(ant::IX_SHORT, ant::IZ_SHORT, K.ez, w1);
+    const V3 Iw2 = axisym(ant::IX_LONG, ant::IZ_LONG, K.zf, w2);
+    const V3 Iwl = axisym(ant::IX_SHORT, ant::IZ_SHORT, K.ez, w);
+    // F = m a - f_ext, N = I alpha + w x I w - tau_ext; f_ext = gravity + Bullet link damping
+    const V3 F_a = ant::M_SHORT * (a_ac + gz) + (P.kl * ant::M_SHORT * (1.f + norm(v_ac))) * v_ac;
+    const V3 N_a = axisym(ant::IX_SHORT, ant::IZ_SHORT, K.ez, al1) + cross(w1, Iw1) + (P.ka * (1.f + norm(w1))) * Iw1;
+    const V3 F_f = ant::M_LONG * (a_fc + gz) + (P.kl * ant::M_LONG * (1.f + norm(v_fc))) * v_fc;
+    const V3 N_f = axisym(ant::IX_LONG, ant::IZ_LONG, K.zf, al2) + cross(w2, Iw2) + (P.ka * (1.f + norm(w2))) * Iw2;
+    const V3 F_l = (P.kl * ant::M_SHORT * (1.f + norm(v_lc))) * v_lc;  // fixed leg link: damping only
+    const V3 N_l = (P.ka * (1.f + norm(w))) * Iwl;
+    const float cb2 = dot(a2, N_f + cross(K.r2, F_f));
+    const float cb1 = dot(a1, N_a + cross(K.r1, F_a) + N_f + cross(rf1, F_f));
+    V3 cF = F_a + F_f + F_l;
+    V3 cT = N_a + cross(r_ac, F_a) + N_f + cross(r_fc, F_f) + N_l + cross(0.5f * K.rh, F_l);
+
+    // leg mass-matrix blocks
+    const V3 lam2 = cross(a2, K.r2), lam1a = cross(a1, K.r1), lam1f = cross(a1, rf1);
+    const V3 If_a1 = axisym(ant::IX_LONG, ant::IZ_LONG, K.zf, a1);
+    const V3 If_a2 = ant::IX_LONG * a2;  // zf _|_ a2
+    const float M22 = ant::M_LONG * dot(lam2, lam2) + ant::IX_LONG;
+    const float M12 = ant::M_LONG * dot(lam1f, lam2) + dot(a1, If_a2);
+    const float M11 = ant::M_SHORT * dot(lam1a, lam1a) + ant::IZ_SHORT + ant::M_LONG * dot(lam1f, lam1f) + dot(a1, If_a1);
+    const float idet = 1.0f / (M11 * M22 - M12 * M12);
+    D.mi11 = M22 * idet; D.mi22 = M11 * idet; D.mi12 = -M12 * idet;
+    const V3 G2f = ant::M_LONG * lam2, G2t = cross(r_fc, G2f) + If_a2;
+    const V3 G1fa = ant::M_SHORT * lam1a, G1ff = ant::M_LONG * lam1f;
+    const V3 G1f = G1fa + G1ff, G1t = cross(r_ac, G1fa) + ant::IZ_SHORT * a1 + cross(r_fc, G1ff) + If_a1;
+    D.G1[0] = G1t.x; D.G1[1] = G1t.y; D.G1[2] = G1t.z; D.G1[3] = G1f.x; D.G1[4] = G1f.y; D.G1[5] = G1f.z;
+    D.G2[0] = G2t.x; D.G2[1] = G2t.y; D.G2[2] = G2t.z; D.G2[3] = G2f.x; D.G2[4] = G2f.y; D.G2[5] = G2f.z;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      D.K0[i] = D.G1[i] * D.mi11 + D.G2[i] * D.mi12;
+      D.K1[i] = D.G1[i] * D.mi12 + D.G2[i] * D.mi22;
+    }
+    // articulated inertia of this leg about O: rigid6(aux) + rigid6(foot) - G Mll^-1 G^T
+    float S[21];
+    {
+      const float ma = ant::M_SHORT, mf = ant::M_LONG;
+      const float da2 = dot(r_ac, r_ac), df2 = dot(r_fc, r_fc);
+      const float dza = ant::IZ_SHORT - ant::IX_SHORT, dzf = ant::IZ_LONG - ant::IX_LONG;
+      const float diag0 = ant::IX_SHORT + ant::IX_LONG + ma * da2 + mf * df2;
+      const float ra[3] = {r_ac.x, r_ac.y, r_ac.z}, rf[3] = {r_fc.x, r_fc.y, r_fc.z};
+      const float za[3] = {K.ez.x, K.ez.y, K.ez.z}, zf[3] = {K.zf.x, K.zf.y, K.zf.z};
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = i; j < 3; j++)
+          S[sym6(i, j)] = (i == j ? diag0 : 0.f) + dza * za[i] * za[j] + dzf * zf[i] * zf[j] - ma * ra[i] * ra[j] - mf * rf[i] * rf[j];
+      const float mdx = ma * ra[0] + mf * rf[0], mdy = ma * ra[1] + mf * rf[1], mdz = ma * ra[2] + mf * rf[2];
+      // upper-right block m [d]x
+      S[sym6(0, 3)] = 0.f;  S[sym6(0, 4)] = -mdz; S[sym6(0, 5)] = mdy;
+      S[sym6(1, 3)] = mdz;  S[sym6(1, 4)] = 0.f;  S[sym6(1, 5)] = -mdx;
+      S[sym6(2, 3)] = -mdy; S[sym6(2, 4)] = mdx;  S[sym6(2, 5)] = 0.f;
+      S[sym6(3, 3)] = ma + mf; S[sym6(3, 4)] = 0.f; S[sym6(3, 5)] = 0.f;
+      S[sym6(4, 4)] = ma + mf; S[sym6(4, 5)] = 0.f; S[sym6(5, 5)] = ma + mf;
+#pragma unroll
+      for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = i; j < 6; j++) S[sym6(i, j)] -= D.K0[i] * D.G1[j] + D.K1[i] * D.G2[j];
+    }
+#pragma unroll
+    for (int i = 0; i < 21; i++) S[i] = gsum(S[i]);
+    {  // + torso with its rigid leg capsules (COM at O)
+      const float dzc = ant::IZ_COMP - ant::IX_COMP;
+      const float za[3] = {K.ez.x, K.ez.y, K.ez.z};
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = i; j < 3; j++) S[sym6(i, j)] += (i == j ? ant::IX_COMP : 0.f) + dzc * za[i] * za[j];
+      S[sym6(3, 3)] += ant::M_COMP; S[sym6(4, 4)] += ant::M_COMP; S[sym6(5, 5)] += ant::M_COMP;
+    }
+    // Cholesky S = L L^T (in place, lower), then L^-1
+    {
+      float L[6][6];
+#pragma unroll
+      for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) L[i][j] = S[sym6(j, i)];
+      float rd[6];
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        float d = L[j][j];
+#pragma unroll
+        for (int kk = 0; kk < j; kk++) d = fmaf(-L[j][kk], L[j][kk], d);
+        rd[j] = rsqrtf(d);
+        L[j][j] = d * rd[j];
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+          float a = L[i][j];
+#pragma unroll
+          for (int kk = 0; kk < j; kk++) a = fmaf(-L[i][kk], L[j][kk], a);
+          L[i][j] = a * rd[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        D.Li[j * (j + 1) / 2 + j] = rd[j];
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+          float a = 0.f;
+#pragma unroll
+          for (int kk = j; kk < i; kk++) a = fmaf(L[i][kk], D.Li[kk * (kk + 1) / 2 + j], a);
+          D.Li[i * (i + 1) / 2 + j] = -a * rd[i];
+        }
+      }
+    }
+    // generalized accelerations
+    const float f1 = tau1 - cb1, f2 = tau2 - cb2;
+    const float y1 = D.mi11 * f1 + D.mi12 * f2, y2 = D.mi12 * f1 + D.mi22 * f2;
+    float fb[6] = {-cT.x, -cT.y, -cT.z, -cF.x, -cF.y, -cF.z};
+#pragma unroll
+    for (int i = 0; i < 6; i++) fb[i] = gsum(fb[i] - (D.G1[i] * y1 + D.G2[i] * y2));
+    {  // torso composite: w x I w, gravity, damping of the torso sphere link
+      const V3 IwT = axisym(ant::IX_COMP, ant::IZ_COMP, K.ez, w);
+      const V3 tT = cross(w, IwT) + (P.ka * (1.f + norm(w)) * ant::I_TORSO) * w;
+      const V3 fT = ant::M_COMP * gz + (P.kl * ant::M_TORSO * (1.f + norm(v))) * v;
+      fb[0] -= tT.x; fb[1] -= tT.y; fb[2] -= tT.z; fb[3] -= fT.x; fb[4] -= fT.y; fb[5] -= fT.z;
+    }
+    float ud[6];
+    sinv_mul(D.Li, fb, ud);
+    float qdd1 = y1, qdd2 = y2;
+#pragma unroll
+    for (int i = 0; i < 6; i++) { qdd1 = fmaf(-D.K0[i], ud[i], qdd1); qdd2 = fmaf(-D.K1[i], ud[i], qdd2); }
+    const float wv[6] = {w.x, w.y, w.z, v.x, v.y, v.z};
+#pragma unroll
+    for (int i = 0; i < 6; i++) ub[i] = clampf(fmaf(P.h, ud[i], wv[i]), P.vmax);
+    u1 = clampf(fmaf(P.h, qdd1, s.qd1), P.vmax);
+    u2 = clampf(fmaf(P.h, qdd2, s.qd2), P.vmax);
+  }
+
+  // ---------------- constraint rows owned by this lane ----------------
+  const float inv_h = 1.0f / P.h;
+  int nL = 0;
+  {
+    const float zero6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float pl1 = s.q1 - ant::HIP_LO, ph1 = ant::HIP_HI - s.q1;
+    const float pl2 = s.q2 - lc.lo2, ph2 = lc.hi2 - s.q2;
+    if (pl1 <= 0.f) { finish_row(rows, lane, nL, D, zero6, 1.f, 0.f, ub, u1, u2, pl1, P.erp_l, inv_h, true); nL++; }
+    if (ph1 <= 0.f) { finish_row(rows, lane, nL, D, zero6, -1.f, 0.f, ub, u1, u2, ph1, P.erp_l, inv_h, true); nL++; }
+    if (pl2 <= 0.f) { finish_row(rows, lane, nL, D, zero6, 0.f, 1.f, ub, u1, u2, pl2, P.erp_l, inv_h, true); nL++; }
+    if (ph2 <= 0.f) { finish_row(rows, lane, nL, D, zero6, 0.f, -1.f, ub, u1, u2, ph2, P.erp_l, inv_h, true); nL++; }
+  }
+  for (int c = 0; c < nC; c++) {
+    const V3 Pr = mk(CAND(c, 0), CAND(c, 1), CAND(c, 2));
+    const V3 n = mk(CAND(c, 3), CAND(c, 4), CAND(c, 5));
+    const float dist = CAND(c, 6), body = CAND(c, 7);
+    V3 t1, t2;
+    plane_space(n, t1, t2);
+    const V3 Ph = Pr - K.rh, Pa = Pr - r_ank;
+#pragma unroll
+    for (int di = 0; di < 3; di++) {
+      const V3 d = di == 0 ? n : (di == 1 ? t1 : t2);
+      const V3 jt = cross(Pr, d);
+      const float JB[6] = {jt.x, jt.y, jt.z, d.x, d.y, d.z};
+      const float j1 = body >= 1.f ? dot(a1, cross(Ph, d)) : 0.f;
+      const float j2 = body >= 2.f ? dot(a2, cross(Pa, d)) : 0.f;
+      finish_row(rows, lane, 2 + 3 * c + di, D, JB, j1, j2, ub, u1, u2, dist, P.erp_c, inv_h, di == 0);
+    }
+  }
+  stat_contacts += nC; stat_limits += nL;
+  __syncwarp();
+
+  // ---------------- projected Gauss-Seidel, Bullet row order ----------------
+  float dvb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, g1 = 0.f, g2 = 0.f;
+  const int gbase = lane & ~3;
+  for (int it = 0; it < P.iters; it++) {
+    // (1) joint-limit rows; Bullet walks the non-contact rows backwards on even iterations
+    for (int idx = 0; idx < 8; idx++) {
+      const int o = (it & 1) ? (idx >> 1) : 3 - (idx >> 1);
+      const int j = (it & 1) ? (idx & 1) : 1 - (idx & 1);
+      const bool mine = (k == o) && (j < nL);
+      if (!__any_sync(HRL_FULL_MASK, mine)) continue;
+      float dl = 0.f;
+      if (mine) {
+        float jd = ROW(j, RF_JL) * g1 + ROW(j, RF_JL + 1) * g2;
+#pragma unroll
+        for (int i = 0; i < 6; i++) jd = fmaf(ROW(j, RF_JB + i), dvb[i], jd);
+        const float lam = ROW(j, RF_LAM);
+        dl = ROW(j, RF_RHS) - jd * ROW(j, RF_DINV);
+        const float sum = lam + dl;
+        if (sum < 0.f) dl = -lam; else if (sum > P.max_imp) dl = P.max_imp - lam;
+        ROW(j, RF_LAM) = lam + dl;
+        g1 = fmaf(ROW(j, RF_Y), dl, g1); g2 = fmaf(ROW(j, RF_Y + 1), dl, g2);
+      }
+      dl = __shfl_sync(HRL_FULL_MASK, dl, gbase | o);
+      if (dl != 0.f) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) dvb[i] = fmaf(ROW_OF(j, RF_WB + i, gbase | o), dl, dvb[i]);
+      }
+    }
+    // (2) contact normals
+    for (int o = 0; o < 4; o++)
+      for (int c = 0; c < HRL_MAXC; c++) {
+        const bool mine = (k == o) && (c < nC);
+        if (!__any_sync(HRL_FULL_MASK, mine)) continue;
+        const int sl = 2 + 3 * c;
+        float dl = 0.f;
+        if (mine) {
+          float jd = ROW(sl, RF_JL) * g1 + ROW(sl, RF_JL + 1) * g2;
+#pragma unroll
+          for (int i = 0; i < 6; i++) jd = fmaf(ROW(sl, RF_JB + i), dvb[i], jd);
+          const float lam = ROW(sl, RF_LAM);
+          dl = ROW(sl, RF_RHS) - jd * ROW(sl, RF_DINV);
+          if (lam + dl < 0.f) dl = -lam;
+          ROW(sl, RF_LAM) = lam + dl;
+          g1 = fmaf(ROW(sl, RF_Y), dl, g1); g2 = fmaf(ROW(sl, RF_Y + 1), dl, g2);
+        }
+        dl = __shfl_sync(HRL_FULL_MASK, dl, gbase | o);
+        if (dl != 0.f) {
+#pragma unroll
+          for (int i = 0; i < 6; i++) dvb[i] = fmaf(ROW_OF(sl, RF_WB + i, gbase | o), dl, dvb[i]);
+        }
+      }
+    // (3) friction pairs with the implicit cone |f| <= mu * lambda_n
+    for (int o = 0; o < 4; o++)
+      for (int c = 0; c < HRL_MAXC; c++) {
+        const int sl = 2 + 3 * c;
+        const bool mine = (k == o) && (c < nC) && (ROW(sl, RF_LAM) > 0.f);
+        if (!__any_sync(HRL_FULL_MASK, mine)) continue;
+        float da = 0.f, db = 0.f;
+        if (mine) {
+          const int sa = sl + 1, sb = sl + 2;
+          float ja = ROW(sa, RF_JL) * g1 + ROW(sa, RF_JL + 1) * g2;
+          float jb = ROW(sb, RF_JL) * g1 + ROW(sb, RF_JL + 1) * g2;
+#pragma unroll
+          for (int i = 0; i < 6; i++) { ja = fmaf(ROW(sa, RF_JB + i), dvb[i], ja); jb = fmaf(ROW(sb, RF_JB + i), dvb[i], jb); }
+          const float la = ROW(sa, RF_LAM), lb = ROW(sb, RF_LAM);
+          float na = la + (ROW(sa, RF_RHS) - ja * ROW(sa, RF_DINV));
+          float nb = lb + (ROW(sb, RF_RHS) - jb * ROW(sb, RF_DINV));
+          const float lim = P.mu * ROW(sl, RF_LAM), len2 = na * na + nb * nb;
+          if (len2 > lim * lim) { const float sc = lim * rsqrtf(len2); na *= sc; nb *= sc; }
+          da = na - la; db = nb - lb;
+          ROW(sa, RF_LAM) = na; ROW(sb, RF_LAM) = nb;
+          g1 = fmaf(ROW(sa, RF_Y), da, fmaf(ROW(sb, RF_Y), db, g1));
+          g2 = fmaf(ROW(sa, RF_Y + 1), da, fmaf(ROW(sb, RF_Y + 1), db, g2));
+        }
+        da = __shfl_sync(HRL_FULL_MASK, da, gbase | o);
+        db = __shfl_sync(HRL_FULL_MASK, db, gbase | o);
+        if (da != 0.f || db != 0.f) {
+#pragma unroll
+          for (int i = 0; i < 6; i++)
+            dvb[i] = fmaf(ROW_OF(sl + 1, RF_WB + i, gbase | o), da, fmaf(ROW_OF(sl + 2, RF_WB + i, gbase | o), db, dvb[i]));
+        }
+      }
+  }
+  __syncwarp();
+
+  // ---------------- apply, clamp, integrate ----------------
+  float dq1 = g1, dq2 = g2;
+#pragma unroll
+  for (int i = 0; i < 6; i++) { dq1 = fmaf(-D.K0[i], dvb[i], dq1); dq2 = fmaf(-D.K1[i], dvb[i], dq2); }
+#pragma unroll
+  for (int i = 0; i < 6; i++) ub[i] = clampf(ub[i] + dvb[i], P.vmax);
+  u1 = clampf(u1 + dq1, P.vmax); u2 = clampf(u2 + dq2, P.vmax);
+  s.w = mk(ub[0], ub[1], ub[2]); s.v = mk(ub[3], ub[4], ub[5]);
+  s.qd1 = u1; s.qd2 = u2;
+  s.O = s.O + P.h * s.v;
+  s.q1 = fmaf(P.h, u1, s.q1); s.q2 = fmaf(P.h, u2, s.q2);
+  {  // q <- exp(w h) * q  (Bullet pQuatUpdateFun with world-frame omega)
+    float ang = norm(s.w);
+    if (ang * P.h > 0.25f * 3.14159265358979323846f) ang = 0.25f * 3.14159265358979323846f / P.h;
+    float kk;
+    if (ang < 0.001f) kk = 0.5f * P.h - P.h * P.h * P.h * 0.020833333333f * ang * ang;
+    else kk = sinf(0.5f * ang * P.h) / ang;
+    const float ax = s.w.x * kk, ay = s.w.y * kk, az = s.w.z * kk, cw = cosf(0.5f * ang * P.h);
+    const float x = s.qx, y = s.qy, z = s.qz, qw = s.qw;
+    float nx = cw * x + ax * qw + ay * z - az * y;
+    float ny = cw * y + ay * qw + az * x - ax * z;
+    float nz = cw * z + az * qw + ax * y - ay * x;
+    float nw = cw * qw - ax * x - ay * y - az * z;
+    const float inv = rsqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+    s.qx = nx * inv; s.qy = ny * inv; s.qz = nz * inv; s.qw = nw * inv;
+  }
+}

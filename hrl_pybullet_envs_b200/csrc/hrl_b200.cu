@@ -1,0 +1,988 @@
+// hrl_b200.cu - fused env-step kernels (sm_100a) and the C-ABI of include/hrl_b200.h.
+//
+// Layout: one 4-lane group per env (lane = leg), 8 envs per warp, one warp per CTA by default so
+// that 4096 envs become 512 CTAs spread over the 148 SMs x 4 schedulers.  Per-warp shared memory
+// holds the constraint rows of the sub-step, the contact candidates, the sensor bins and an
+// observation staging tile that is written back with fully coalesced stores.
+// No CPU fallback: every entry point fails with HRL_E_CUDA when no device / kernel is available.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "../../include/hrl_b200.h"
+#include "hrl_ant.cuh"
+#include "hrl_math.cuh"
+#include "hrl_sensors.cuh"
+
+#ifndef HRL_WARPS_PER_CTA
+#define HRL_WARPS_PER_CTA 1
+#endif
+#define HRL_OBS_STAGE 64  // floats per env in the staging tile (max obs dim 60)
+
+// ------------------------------------------------------------------------------------------
+// device state (internal SoA layout; the public layout of hrl_get_state is converted by kernels)
+// ------------------------------------------------------------------------------------------
+struct DevState {
+  float4* base;   // [N][4]: (pos.xyz, initial_z) (quat xyzw) (vel.xyz, potential) (ang.xyz, wtd)
+  float4* leg;    // [N][4 legs]: (q_hip, q_ankle, qd_hip, qd_ankle)
+  float4* items;  // [N][4 lanes][2]: items 4k..4k+3 as (x0,y0,x1,y1)(x2,y2,x3,y3)
+  float4* miscf;  // [N][2]: (target.x, target.y, -, -) (feet0..3)
+  int4* misci;    // [N][2]: (t, episode, steps_total, goals_left) (since, rewarded, -, -)
+  unsigned long long* stats;  // [4]: contacts, limit rows, env-substeps, non-finite resets
+};
+
+struct hrl_handle {
+  hrl_config cfg;
+  int device, N, D, A;
+  DevState st;
+  float* d_bounds;  // lidar bound lines [7][4]
+  int n_lines;
+  // staging for hrl_step_host
+  float *s_act, *s_obs, *s_rew, *s_info;
+  uint8_t* s_done;
+};
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int set_err(int code, const char* msg) {
+  snprintf(g_err, sizeof g_err, "%s", msg);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof g_err, "%s: %s", where, cudaGetErrorString(e));
+  return HRL_E_CUDA;
+}
+#define CK(call)                                    \
+  do {                                              \
+    cudaError_t _e = (call);                        \
+    if (_e != cudaSuccess) return cuda_fail(_e, #call); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// task-layer helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float clip5(float x) { return fminf(fmaxf(x, -5.f), 5.f); }
+
+// Flagrun goal j of episode ep: ant_flagrun_env.py:71-78; the stream is shared by all envs (:39)
+__device__ __forceinline__ void flag_goal(const hrl_config& cfg, int ep, int j, float& gx, float& gy) {
+  const float half = cfg.flag_size * 0.5f;
+  for (uint32_t attempt = 0;; attempt++) {
+    float u[4];
+    rng_u4(cfg.flag_seed, 0u, STREAM_FLAG, attempt, (uint32_t)(ep * 128 + j), u);
+    gx = -half + 2.f * half * u[0]; gy = -half + 2.f * half * u[1];
+    if (sqrtf(gx * gx + gy * gy) < 0.5f && attempt + 1 < HRL_MAX_PLACE_ATTEMPTS) continue;
+    return;
+  }
+}
+
+// gather_scene.py:52-62: uniform on the (size-1)^2 square, rejected while closer than `spacing`
+// to (ax, ay).  Evaluated in double from 24-bit uniforms and rounded to f32 (bit-identical to the oracle).
+__device__ __forceinline__ void place_item(const hrl_config& cfg, uint32_t genv, uint32_t stream, uint32_t draw,
+                                           int item, float ax, float ay, float& ox, float& oy) {
+  const double sx = (double)cfg.world_size[0] - 1.0, sy = (double)cfg.world_size[1] - 1.0;
+  for (int attempt = 0;; attempt++) {
+    float u[4];
+    rng_u4(cfg.seed, genv, stream, draw, (uint32_t)(item * 64 + attempt), u);
+    double x = (double)u[0] * sx - sx / 2, y = (double)u[1] * sy - sy / 2;
+    double dx = (double)ax - x, dy = (double)ay - y;
+    if (sqrt(dx * dx + dy * dy) < (double)cfg.robot_object_spacing && attempt + 1 < HRL_MAX_PLACE_ATTEMPTS) continue;
+    ox = (float)x; oy = (float)y;
+    return;
+  }
+}
+
+struct TaskRegs {  // replicated per-env task state held in registers
+  float initial_z, potential, wtd, tx, ty;
+  float feet[4];
+  int t, episode, steps_total, goals_left, since, rewarded;
+};
+
+// ------------------------------------------------------------------------------------------
+// fused Ant step kernel
+//   FAMILY 0: AntGather.  FAMILY 1: walker family (AntMaze, AntFlagrun, AntMj, AntMazeMj).
+//   mode 0: full env step (+ auto-reset), mode 1: n_sub physics sub-steps only,
+//   mode 2: reset the masked envs and emit their observation, mode 3: observe only.
+// ------------------------------------------------------------------------------------------
+#define SMEM_PER_WARP_FLOATS (HRL_SMEM_FLOATS_PER_WARP + 8 * HRL_OBS_STAGE + 2 * 8 * 2 * HRL_MAX_BINS)
+
+template <int FAMILY>
+__global__ void __launch_bounds__(32 * HRL_WARPS_PER_CTA)
+ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float* __restrict__ bounds, int n_lines,
+               const float* __restrict__ actions, const uint8_t* __restrict__ mask, float* __restrict__ obs_out,
+               float* __restrict__ rew_out, uint8_t* __restrict__ done_out, float* __restrict__ info_out,
+               float* __restrict__ term_out, int mode, int n_sub, int D) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, k = lane & 3, ew = lane >> 2;
+  float* rows = smem + warp * SMEM_PER_WARP_FLOATS;
+  float* cands = rows + HRL_NSLOT * RF_N * 32;
+  float* sobs = cands + HRL_MAXC * HRL_CAND_F * 32;                               // [8][HRL_OBS_STAGE]
+  unsigned long long* sbins = (unsigned long long*)(sobs + 8 * HRL_OBS_STAGE);   // [8][2][HRL_MAX_BINS]
+  const int N = cfg.num_envs, kind = cfg.env_kind;
+  const int env_raw = (blockIdx.x * (32 * HRL_WARPS_PER_CTA) + threadIdx.x) >> 2;
+  const bool active = env_raw < N;
+  const int e = active ? env_raw : N - 1;
+  const int env0 = (blockIdx.x * (32 * HRL_WARPS_PER_CTA) + warp * 32) >> 2;  // first env of this warp
+  const uint32_t genv = (uint32_t)(cfg.env_index_offset + e);
+  const LegConst lc = leg_const(k);
+
+  // ---- load ----
+  AntLane s;
+  TaskRegs T;
+  {
+    const float4 b0 = st.base[e * 4 + 0], b1 = st.base[e * 4 + 1], b2 = st.base[e * 4 + 2], b3 = st.base[e * 4 + 3];
+    const float4 lg = st.leg[e * 4 + k];
+    const float4 m0 = st.miscf[e * 2 + 0], m1 = st.miscf[e * 2 + 1];
+    const int4 i0 = st.misci[e * 2 + 0], i1 = st.misci[e * 2 + 1];
+    s.O = mk(b0.x, b0.y, b0.z); T.initial_z = b0.w;
+    s.qx = b1.x; s.qy = b1.y; s.qz = b1.z; s.qw = b1.w;
+    s.v = mk(b2.x, b2.y, b2.z); T.potential = b2.w;
+    s.w = mk(b3.x, b3.y, b3.z); T.wtd = b3.w;
+    s.q1 = lg.x; s.q2 = lg.y; s.qd1 = lg.z; s.qd2 = lg.w;
+    T.tx = m0.x; T.ty = m0.y;
+    T.feet[0] = m1.x; T.feet[1] = m1.y; T.feet[2] = m1.z; T.feet[3] = m1.w;
+    T.t = i0.x; T.episode = i0.y; T.steps_total = i0.z; T.goals_left = i0.w; T.since = i1.x; T.rewarded = i1.y;
+  }
+  float it_x[4], it_y[4];
+  if (FAMILY == 0) {
+    const float4 a = st.items[(e * 4 + k) * 2 + 0], b = st.items[(e * 4 + k) * 2 + 1];
+    it_x[0] = a.x; it_y[0] = a.y; it_x[1] = a.z; it_y[1] = a.w; it_x[2] = b.x; it_y[2] = b.y; it_x[3] = b.z; it_y[3] = b.w;
+  }
+
+  // ---- physics ----
+  float act1 = 0.f, act2 = 0.f;
+  int feet_ground = 0;
+  if (mode <= 1) {
+    const float2 a = reinterpret_cast<const float2*>(actions)[e * 4 + k];
+    act1 = a.x; act2 = a.y;
+    // WalkerBase.apply_action [3P-MEM]: clip to +-1, torque = power * power_coef * a
+    const float tau1 = cfg.torque_scale * fminf(fmaxf(act1, -1.f), 1.f);
+    const float tau2 = cfg.torque_scale * fminf(fmaxf(act2, -1.f), 1.f);
+    const SubstepParams P = make_params(cfg);
+    int sc = 0, sl = 0;
+    const int ns = mode == 0 ? cfg.substeps : n_sub;
+    for (int i = 0; i < ns; i++) {
+      const bool on = (i == 0) || !cfg.torque_first_substep_only;
+      ant_substep(s, P, lc, on ? tau1 : 0.f, on ? tau2 : 0.f, rows, cands, lane, k, feet_ground, sc, sl);
+    }
+    if (st.stats && active) {
+      sc = __reduce_add_sync(HRL_FULL_MASK, sc); sl = __reduce_add_sync(HRL_FULL_MASK, sl);
+      if (lane == 0) {
+        atomicAdd(&st.stats[0], (unsigned long long)sc); atomicAdd(&st.stats[1], (unsigned long long)sl);
+        atomicAdd(&st.stats[2], (unsigned long long)(ns * 8));
+      }
+    }
+  }
+
+  // ---- task layer: observation / reward / done / reset state machine ----
+  // todo: 0 nothing, 1 compose+commit obs, 2 Flagrun reset stage 1 (stale-target calc_state)
+  int todo = (mode == 1) ? 0 : 1;
+  bool first = (mode == 0);       // first compose of a full step carries the reward logic
+  bool set_pot = false;           // potential <- -wtd/dt when the obs is committed (walker reset)
+  int done = 0;
+  if (mode == 2) {
+    const bool m = mask ? (mask[e] != 0) : true;
+    todo = m ? 3 : 0;  // 3: reset request
+  }
+
+  for (int guard = 0; guard < 5; guard++) {
+    // reset requests are executed first (register state only)
+    if (todo == 3) {
+      T.t = 0;
+      s.O = mk(cfg.start_pos[0], cfg.start_pos[1], cfg.start_pos[2]);
+      s.qx = s.qy = s.qz = 0.f; s.qw = 1.f;
+      s.v = mk(0.f, 0.f, 0.f); s.w = mk(0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 4; i++) T.feet[i] = 0.f;
+      {  // WalkerBase.robot_specific_reset: joints ~ U(-0.1, 0.1), zero velocity
+        float u[4];
+        rng_u4(cfg.seed, genv, STREAM_JOINT, (uint32_t)T.episode, (uint32_t)(k >> 1), u);
+        s.q1 = -0.1f + 0.2f * u[(k & 1) * 2]; s.q2 = -0.1f + 0.2f * u[(k & 1) * 2 + 1];
+        s.qd1 = 0.f; s.qd2 = 0.f;
+      }
+      T.initial_z = s.O.z;
+      if (FAMILY == 0) {
+        // gather_scene.py:38-50: every item re-randomised, avoiding (0,0)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int gi = 4 * k + i;
+          if (gi < cfg.n_food + cfg.n_poison) place_item(cfg, genv, STREAM_ITEM_RESET, (uint32_t)T.episode, gi, 0.f, 0.f, it_x[i], it_y[i]);
+        }
+        T.tx = 0.f; T.ty = 0.f;
+        todo = 1;
+      } else {
+        if (kind == HRL_ANT_MAZE || kind == HRL_ANT_MAZE_MJ) {
+          float u[4];
+          rng_u4(cfg.seed, genv, STREAM_GOAL, (uint32_t)T.episode, 0u, u);
+          int idx = (int)(u[0] * (float)cfg.n_targets);  // rs.randint(0, len(targets)) ant_maze_bullet_env.py:110
+          if (idx >= cfg.n_targets) idx = cfg.n_targets - 1;
+          T.tx = cfg.targets[idx][0]; T.ty = cfg.targets[idx][1];
+        }
+        if (kind == HRL_ANT_MJ) { T.tx = 1000.f; T.ty = 0.f; }
+        if (kind == HRL_ANT_FLAGRUN) {
+          if (T.episode == 0) { T.tx = 1000.f; T.ty = 0.f; }  // WalkerBase default walk target
+          T.goals_left = cfg.flag_max_targets; T.rewarded = 0;
+          todo = 2;
+        } else { set_pot = true; todo = 1; }
+      }
+      T.episode++;
+    }
+    if (!__any_sync(HRL_FULL_MASK, todo != 0)) break;
+
+    // ---------------- calc_state of the current register state ----------------
+    float roll, pitch, yaw;
+    quat_to_rpy(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);
+    float sy_, cy_;
+    sincosf(-yaw, &sy_, &cy_);
+    const float vbx = cy_ * s.v.x - sy_ * s.v.y, vby = sy_ * s.v.x + cy_ * s.v.y;
+    const float o_z = clip5(s.O.z - T.initial_z);
+    const float o_v0 = clip5(0.3f * vbx), o_v1 = clip5(0.3f * vby), o_v2 = clip5(0.3f * s.v.z);
+    const float o_r = clip5(roll), o_p = clip5(pitch);
+    const float mid2 = 0.5f * (lc.lo2 + lc.hi2);
+    const float rel1 = 2.f * s.q1 / (ant::HIP_HI - ant::HIP_LO), rel2 = 2.f * (s.q2 - mid2) / (lc.hi2 - lc.lo2);
+    const float sp1 = 0.1f * s.qd1, sp2 = 0.1f * s.qd2;
+    float wtd_new = 0.f, sin_t = 0.f, cos_t = 1.f;
+    if (FAMILY == 1) {
+      // body_xyz = mean over the 13 link COMs (+ scene bodies, quirk Q1)
+      const LegKin K = leg_fk(s, lc);
+      const V3 part = 2.5f * K.rh + 3.f * K.r1 + K.r2;  // (leg + aux + foot COMs) - 3 O
+      const float sx = gsum(part.x) + 13.f * s.O.x + cfg.scene_parts_sum[0];
+      const float sy = gsum(part.y) + 13.f * s.O.y + cfg.scene_parts_sum[1];
+      const float inv_np = 1.0f / (float)(13 + cfg.n_scene_parts);
+      const float bx = sx * inv_np, by = sy * inv_np;
+      const float dx = T.tx - bx, dy = T.ty - by;
+      wtd_new = sqrtf(dx * dx + dy * dy);
+      sincosf(atan2f(dy, dx) - yaw, &sin_t, &cos_t);
+    }
+    float* so = sobs + ew * HRL_OBS_STAGE;
+    const bool commit = (todo == 1);
+    int fin = 1;       // finite flag (this lane's values)
+    int switched = 0;  // Flagrun: the target changed in this step
+
+    if (FAMILY == 0) {
+      // ---------------- AntGather: ant_gather_env.py:76-119 ----------------
+      float food_rew = 0.f;
+      if (first && todo == 1) {
+        // pickups in item order; each lane owns 4 items (:86-92, gather_scene.py:95-114)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int gi = 4 * k + i;
+          if (gi >= cfg.n_food + cfg.n_poison) continue;
+          const double dx = __dsub_rn((double)it_x[i], (double)s.O.x), dy = __dsub_rn((double)it_y[i], (double)s.O.y);
+          const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+          if (d2 < (double)cfg.robot_coll_dist) {
+            food_rew += (gi < cfg.n_food) ? 1.f : -1.f;
+            if (cfg.respawn) place_item(cfg, genv, STREAM_ITEM, (uint32_t)T.steps_total, gi, s.O.x, s.O.y, it_x[i], it_y[i]);
+            else { it_x[i] = 100.f; it_y[i] = 0.f; }  // fake_kill_pos gather_scene.py:13
+          }
+        }
+      }
+      food_rew = gsum(food_rew);
+      // sector sensor (:128-177): nearest item wins per bin
+      const int nb = cfg.n_bins;
+      for (int i = lane; i < 8 * 2 * HRL_MAX_BINS; i += 32) sbins[i] = 0x7ff0000000000000ull;
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int gi = 4 * k + i;
+        if (gi >= cfg.n_food + cfg.n_poison) continue;
+        double d2;
+        const int b = gather_item_bin(s.O.x, s.O.y, yaw, it_x[i], it_y[i], nb, cfg.sensor_range, cfg.sensor_span, &d2);
+        if (b >= 0) atomicMin(&sbins[(ew * 2 + (gi < cfg.n_food ? 0 : 1)) * HRL_MAX_BINS + b], (unsigned long long)__double_as_longlong(d2));
+      }
+      __syncwarp();
+      if (commit) {
+        if (k == 0) {
+          so[0] = o_z; so[1] = o_v0; so[2] = o_v1; so[3] = o_v2; so[4] = o_r; so[5] = o_p;
+          so[22] = T.feet[0]; so[23] = T.feet[1]; so[24] = T.feet[2]; so[25] = T.feet[3];
+        }
+        so[6 + 4 * k] = clip5(rel1); so[7 + 4 * k] = clip5(sp1); so[8 + 4 * k] = clip5(rel2); so[9 + 4 * k] = clip5(sp2);
+        for (int b = k; b < 2 * nb; b += 4) {
+          const int ty = b / nb, bb = b - ty * nb;
+          const unsigned long long bits = sbins[(ew * 2 + ty) * HRL_MAX_BINS + bb];
+          so[26 + b] = bits == 0x7ff0000000000000ull ? 0.f : (float)(1.0 - __longlong_as_double((long long)bits) / (double)cfg.sensor_range);
+        }
+      }
+      fin = isfinite(o_z) && isfinite(o_v0) && isfinite(o_v1) && isfinite(o_v2) && isfinite(o_r) && isfinite(o_p) &&
+            isfinite(rel1) && isfinite(sp1) && isfinite(rel2) && isfinite(sp2);
+      fin = (gsum(fin ? 0.f : 1.f) == 0.f);
+      if (first && todo == 1) {
+        const int alive = (o_z + T.initial_z) > 0.26f;  // Ant.alive_bonus on state[0] + initial_z (:99)
+        done = !alive || !fin;                          // :100-103
+        const float dead_rew = alive ? 0.f : cfg.dying_cost;
+        T.t++; T.steps_total++;
+        float trunc = 0.f;
+        if (cfg.max_episode_steps > 0 && T.t >= cfg.max_episode_steps) { trunc = done ? 0.f : 1.f; done = 1; }
+        if (active && k == 0) {
+          rew_out[e] = food_rew + dead_rew;
+          done_out[e] = (uint8_t)done;
+          if (info_out) reinterpret_cast<float4*>(info_out)[e] = make_float4(food_rew, dead_rew, trunc, (float)T.t);
+        }
+      }
+    } else {
+      // ---------------- walker family ----------------
+      const bool mj = (kind == HRL_ANT_MJ || kind == HRL_ANT_MAZE_MJ);
+      if (commit) {
+        if (mj) {
+          // MjAnt.calc_state envs/MjAnt.py:17-25: [pos3, quat4, q8, lin3, ang3, qd8] unclipped
+          if (k == 0) {
+            so[0] = s.O.x; so[1] = s.O.y; so[2] = s.O.z; so[3] = s.qx; so[4] = s.qy; so[5] = s.qz; so[6] = s.qw;
+            so[15] = s.v.x; so[16] = s.v.y; so[17] = s.v.z; so[18] = s.w.x; so[19] = s.w.y; so[20] = s.w.z;
+          }
+          so[7 + 2 * k] = s.q1; so[8 + 2 * k] = s.q2; so[21 + 2 * k] = s.qd1; so[22 + 2 * k] = s.qd2;
+          if (kind == HRL_ANT_MAZE_MJ) {  // ant_maze_mj_env.py:57-64
+            const int nb = cfg.n_bins;
+            for (int b = k; b < nb; b += 4) {
+              so[29 + b] = lidar_ray(b, nb, cfg.sensor_span, cfg.sensor_range, n_lines, bounds, s.O.x, s.O.y, yaw);
+              so[29 + nb + b] = 0.f; so[29 + 2 * nb + b] = 0.f;
+            }
+            if (k == 0) so[29 + 3 * nb] = (float)T.t * 0.001f;
+          }
+        } else {
+          const int off = (kind == HRL_ANT_FLAGRUN) ? 2 : 0;  // Flagrun keeps sin/cos of the target angle
+          if (k == 0) {
+            so[0] = o_z;
+            if (off) { so[1] = clip5(sin_t); so[2] = clip5(cos_t); }
+            so[1 + off] = o_v0; so[2 + off] = o_v1; so[3 + off] = o_v2; so[4 + off] = o_r; so[5 + off] = o_p;
+            so[22 + off] = T.feet[0]; so[23 + off] = T.feet[1]; so[24 + off] = T.feet[2]; so[25 + off] = T.feet[3];
+          }
+          so[6 + off + 4 * k] = clip5(rel1); so[7 + off + 4 * k] = clip5(sp1);
+          so[8 + off + 4 * k] = clip5(rel2); so[9 + off + 4 * k] = clip5(sp2);
+          if (kind == HRL_ANT_MAZE) {
+            if (k == 0) {  // ant_maze_bullet_env.py:123-133 (true torso xy, not the Q1 mean)
+              const float vx = T.tx - s.O.x, vy = T.ty - s.O.y;
+              if (cfg.target_encoding == 0) { const float nn = sqrtf(vx * vx + vy * vy); so[26] = vx / nn; so[27] = vy / nn; }
+              else { float sa, ca; sincosf(atan2f(vy, vx) - yaw, &sa, &ca); so[26] = sa; so[27] = ca; }
+            }
+            if (cfg.sense_walls)
+              for (int b = k; b < cfg.n_bins; b += 4)
+                so[28 + b] = lidar_ray(b, cfg.n_bins, cfg.sensor_span, cfg.sensor_range, n_lines, bounds, s.O.x, s.O.y, yaw);
+          }
+        }
+      }
+      if (todo == 2) {
+        // Flagrun reset stage 1 (ant_flagrun_env.py:141-153): calc_state with the STALE target,
+        // then next_target(): potential from that stale distance (quirk Q3)
+        T.wtd = wtd_new;
+        T.goals_left--;
+        flag_goal(cfg, T.episode - 1, T.goals_left, T.tx, T.ty);
+        T.rewarded = 0;
+        T.potential = -T.wtd / cfg.dt;
+      }
+      if (commit) {
+        T.wtd = wtd_new;
+        if (set_pot) { T.potential = -T.wtd / cfg.dt; set_pot = false; }
+      }
+      if (first && todo == 1) {
+        // WalkerBaseBulletEnv.step [3P-MEM] / AntMjEnv.step envs/MjAnt.py:36-97
+        fin = mj ? (isfinite(s.q1) && isfinite(s.q2) && isfinite(s.qd1) && isfinite(s.qd2) && isfinite(s.O.x + s.O.y + s.O.z) &&
+                    isfinite(s.qx + s.qy + s.qz + s.qw) && isfinite(s.v.x + s.v.y + s.v.z) && isfinite(s.w.x + s.w.y + s.w.z))
+                 : (isfinite(o_z) && isfinite(sin_t) && isfinite(cos_t) && isfinite(o_v0) && isfinite(o_v1) && isfinite(o_v2) &&
+                    isfinite(o_r) && isfinite(o_p) && isfinite(rel1) && isfinite(sp1) && isfinite(rel2) && isfinite(sp2));
+        fin = (gsum(fin ? 0.f : 1.f) == 0.f);
+        const int alive = mj ? (s.O.z > 0.26f) : ((o_z + T.initial_z) > 0.26f);
+        done = !alive || !fin;
+        const float pot_old = T.potential;
+        T.potential = -T.wtd / cfg.dt;
+        const float progress = T.potential - pot_old;
+        const float elec = gsum(fabsf(act1 * sp1) + fabsf(act2 * sp2)) * 0.125f;  // joint_speeds are unclipped
+        const float sq = gsum(act1 * act1 + act2 * act2) * 0.125f;
+        const float nlim = gsum((fabsf(rel1) > 0.99f ? 1.f : 0.f) + (fabsf(rel2) > 0.99f ? 1.f : 0.f));
+        const float electricity = mj ? 0.f : (cfg.electricity_cost * elec + cfg.stall_torque_cost * sq);
+        const float inner = (alive ? 1.f : -1.f) + progress + electricity + cfg.joints_at_limit_cost * nlim;
+        // quirk Q2: feet flags measured in this step appear in the NEXT observation
+#pragma unroll
+        for (int j = 0; j < 4; j++) T.feet[j] = (float)__shfl_sync(HRL_FULL_MASK, feet_ground, (lane & ~3) | j);
+        float rew = inner, info1 = 0.f;
+        int next = 0;
+        if (kind == HRL_ANT_MAZE || kind == HRL_ANT_MAZE_MJ) {
+          rew = inner * cfg.inner_rew_weight;  // ant_maze_bullet_env.py:84, ant_maze_mj_env.py:73
+          if (T.wtd < cfg.tol && (cfg.done_at_target || kind == HRL_ANT_MAZE_MJ)) { rew += 1.f; done = 1; }
+        } else if (kind == HRL_ANT_FLAGRUN) {
+          // ant_flagrun_env.py:162-204
+          T.since += 1;
+          if (T.wtd < cfg.tol) {
+            if (!T.rewarded) { rew += cfg.goal_reach_rew; T.rewarded = 1; }
+            if (T.goals_left > 0) {
+              T.goals_left--; flag_goal(cfg, T.episode - 1, T.goals_left, T.tx, T.ty);
+              T.rewarded = 0; T.potential = -T.wtd / cfg.dt; T.since = 0; next = 1;
+            } else done = 1;
+          }
+          if (cfg.flag_timeout > 0 && cfg.flag_timeout <= T.since) {
+            if (T.goals_left > 0) {
+              T.goals_left--; flag_goal(cfg, T.episode - 1, T.goals_left, T.tx, T.ty);
+              T.rewarded = 0; T.potential = -T.wtd / cfg.dt; T.since = 0; next = 1;
+            } else done = 1;
+          }
+          info1 = (float)T.goals_left;
+        }
+        T.t++; T.steps_total++;
+        float trunc = 0.f;
+        if (cfg.max_episode_steps > 0 && T.t >= cfg.max_episode_steps) { trunc = done ? 0.f : 1.f; done = 1; }
+        if (active && k == 0) {
+          rew_out[e] = rew;
+          done_out[e] = (uint8_t)done;
+          if (info_out) reinterpret_cast<float4*>(info_out)[e] = make_float4(inner, info1, trunc, (float)T.t);
+        }
+        switched = next;
+      }
+    }
+    // ---------------- terminal obs + reset decision (only after the post-physics compose) ----------------
+    int next_todo = 0;
+    if (todo == 2) next_todo = 1;
+    if (first && todo == 1) {
+      if (switched) next_todo = 1;  // fresh calc_state with the new target (ant_flagrun_env.py:120,190)
+      if (done && cfg.auto_reset) next_todo = 3;
+    }
+    const unsigned need_mask = __ballot_sync(HRL_FULL_MASK, next_todo == 3);
+    if (need_mask && term_out) {
+      __syncwarp();
+      for (int i = lane; i < 8 * D; i += 32) {
+        const int w8 = i / D, c = i - w8 * D;
+        if (((need_mask >> (4 * w8)) & 1u) && env0 + w8 < N) term_out[(size_t)(env0 + w8) * D + c] = sobs[w8 * HRL_OBS_STAGE + c];
+      }
+      __syncwarp();
+    }
+    first = false;
+    todo = next_todo;
+  }
+
+  // ---- store ----
+  if (active) {
+    if (k == 0) {
+      st.base[e * 4 + 0] = make_float4(s.O.x, s.O.y, s.O.z, T.initial_z);
+      st.base[e * 4 + 1] = make_float4(s.qx, s.qy, s.qz, s.qw);
+      st.base[e * 4 + 2] = make_float4(s.v.x, s.v.y, s.v.z, T.potential);
+      st.base[e * 4 + 3] = make_float4(s.w.x, s.w.y, s.w.z, T.wtd);
+      st.miscf[e * 2 + 0] = make_float4(T.tx, T.ty, 0.f, 0.f);
+      st.miscf[e * 2 + 1] = make_float4(T.feet[0], T.feet[1], T.feet[2], T.feet[3]);
+      st.misci[e * 2 + 0] = make_int4(T.t, T.episode, T.steps_total, T.goals_left);
+      st.misci[e * 2 + 1] = make_int4(T.since, T.rewarded, 0, 0);
+    }
+    st.leg[e * 4 + k] = make_float4(s.q1, s.q2, s.qd1, s.qd2);
+    if (FAMILY == 0) {
+      st.items[(e * 4 + k) * 2 + 0] = make_float4(it_x[0], it_y[0], it_x[1], it_y[1]);
+      st.items[(e * 4 + k) * 2 + 1] = make_float4(it_x[2], it_y[2], it_x[3], it_y[3]);
+    }
+  }
+  if (mode != 1 && obs_out) {
+    __syncwarp();
+    // coalesced write-back of the staged observation rows (8 consecutive envs = one contiguous span)
+    unsigned wmask = 0xffffffffu;
+    if (mode == 2) {
+      const bool m = mask ? (mask[e] != 0) : true;
+      wmask = __ballot_sync(HRL_FULL_MASK, m);
+    }
+    for (int i = lane; i < 8 * D; i += 32) {
+      const int w8 = i / D, c = i - w8 * D;
+      if (env0 + w8 < N && ((wmask >> (4 * w8)) & 1u)) obs_out[(size_t)(env0 + w8) * D + c] = sobs[w8 * HRL_OBS_STAGE + c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// PointGather: one thread per env (point_bot.py, gather_base.py:74-109).  The cube only
+// translates (north star: "the PointGather point-mass integrator"); state lives in the same
+// DevState arrays (base rows 0/2, items).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void point_substep(V3& pos, V3& vel, V3 force, const SubstepParams& P) {
+  const float m = pointbot::MASS, half = pointbot::HALF;
+  const float wx = P.wx - half, wy = P.wy - half;
+  V3 Nn[5]; float Dd[5]; int nc = 0;
+  const float dg = pos.z - half - P.gz;
+  if (dg < P.margin) { Nn[nc] = mk(0.f, 0.f, 1.f); Dd[nc++] = dg; }
+  if (P.has_walls) {
+    if (wx - pos.x < P.margin) { Nn[nc] = mk(-1.f, 0.f, 0.f); Dd[nc++] = wx - pos.x; }
+    if (pos.x + wx < P.margin) { Nn[nc] = mk(1.f, 0.f, 0.f); Dd[nc++] = pos.x + wx; }
+    if (wy - pos.y < P.margin) { Nn[nc] = mk(0.f, -1.f, 0.f); Dd[nc++] = wy - pos.y; }
+    if (pos.y + wy < P.margin) { Nn[nc] = mk(0.f, 1.f, 0.f); Dd[nc++] = pos.y + wy; }
+  }
+  V3 f = mk(force.x, force.y, force.z - m * P.g) + (-m * (P.kl + P.kl * norm(vel))) * vel;
+  V3 v = vel + (P.h / m) * f;
+  v = mk(clampf(v.x, P.vmax), clampf(v.y, P.vmax), clampf(v.z, P.vmax));
+  float lamn[5], lama[5], lamb[5], rhsn[5], rhsa[5], rhsb[5];
+  V3 T1[5], T2[5];
+  const float inv_h = 1.0f / P.h;
+  for (int c = 0; c < nc; c++) {
+    const float rel = dot(Nn[c], v);
+    float posErr = 0.f, velErr = -rel;
+    if (Dd[c] > 0.f) velErr -= Dd[c] * inv_h; else posErr = -Dd[c] * P.erp_c * inv_h;
+    rhsn[c] = (posErr + velErr) * m;
+    plane_space(Nn[c], T1[c], T2[c]);
+    rhsa[c] = -dot(T1[c], v) * m; rhsb[c] = -dot(T2[c], v) * m;
+    lamn[c] = lama[c] = lamb[c] = 0.f;
+  }
+  V3 dv = mk(0.f, 0.f, 0.f);
+  for (int it = 0; it < P.iters; it++) {
+    for (int c = 0; c < nc; c++) {
+      float dl = rhsn[c] - dot(Nn[c], dv) * m;
+      if (lamn[c] + dl < 0.f) dl = -lamn[c];
+      lamn[c] += dl; dv = dv + (dl / m) * Nn[c];
+    }
+    for (int c = 0; c < nc; c++) {
+      if (!(lamn[c] > 0.f)) continue;
+      float sa = lama[c] + rhsa[c] - dot(T1[c], dv) * m, sb = lamb[c] + rhsb[c] - dot(T2[c], dv) * m;
+      const float lim = P.mu * lamn[c], len2 = sa * sa + sb * sb;
+      if (len2 > lim * lim) { const float sc = lim * rsqrtf(len2); sa *= sc; sb *= sc; }
+      const float da = sa - lama[c], db = sb - lamb[c];
+      lama[c] = sa; lamb[c] = sb;
+      dv = dv + (da / m) * T1[c] + (db / m) * T2[c];
+    }
+  }
+  vel = v + dv;
+  pos = pos + P.h * vel;
+}
+
+__global__ void __launch_bounds__(128)
+point_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float* __restrict__ actions,
+                 const uint8_t* __restrict__ mask, float* __restrict__ obs_out, float* __restrict__ rew_out,
+                 uint8_t* __restrict__ done_out, float* __restrict__ info_out, float* __restrict__ term_out, int mode,
+                 int n_sub, int D) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= cfg.num_envs) return;
+  const uint32_t genv = (uint32_t)(cfg.env_index_offset + e);
+  float4 b0 = st.base[e * 4 + 0], b2 = st.base[e * 4 + 2];
+  int4 i0 = st.misci[e * 2 + 0];
+  V3 pos = mk(b0.x, b0.y, b0.z), vel = mk(b2.x, b2.y, b2.z);
+  float initial_z = b0.w;
+  float ix[16], iy[16];
+#pragma unroll
+  for (int l = 0; l < 8; l++) {
+    const float4 a = st.items[e * 8 + l];
+    ix[2 * l] = a.x; iy[2 * l] = a.y; ix[2 * l + 1] = a.z; iy[2 * l + 1] = a.w;
+  }
+  const int n_items = cfg.n_food + cfg.n_poison, nb = cfg.n_bins;
+  if (mode <= 1) {
+    // point_bot.py:28-31: F = a/|a| * 500 N in the world frame (NaN for a == 0: kept, see gather_base.py:99-101)
+    const float ax = actions[e * 2], ay = actions[e * 2 + 1], nn = sqrtf(ax * ax + ay * ay);
+    const V3 F = mk(ax / nn * cfg.torque_scale, ay / nn * cfg.torque_scale, 0.f), Z = mk(0.f, 0.f, 0.f);
+    const SubstepParams P = make_params(cfg);
+    const int ns = mode == 0 ? cfg.substeps : n_sub;
+    for (int i = 0; i < ns; i++) point_substep(pos, vel, (i == 0 || !cfg.torque_first_substep_only) ? F : Z, P);
+  }
+  bool do_reset = false, emit = (mode != 1);
+  if (mode == 2) { do_reset = mask ? mask[e] != 0 : true; emit = do_reset; }
+  float food_rew = 0.f;
+  int done = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    if (do_reset) {
+      i0.x = 0;
+      pos = mk(cfg.start_pos[0], cfg.start_pos[1], cfg.start_pos[2]); vel = mk(0.f, 0.f, 0.f);  // point_bot.py:12,25-26
+      initial_z = 1.f;                                                                            // point_bot.py:18
+      for (int gi = 0; gi < n_items; gi++) place_item(cfg, genv, STREAM_ITEM_RESET, (uint32_t)i0.y, gi, 0.f, 0.f, ix[gi], iy[gi]);
+      i0.y++;
+      do_reset = false;
+    }
+    if (mode == 0 && pass == 0) {
+      for (int gi = 0; gi < n_items; gi++) {
+        const double dx = __dsub_rn((double)ix[gi], (double)pos.x), dy = __dsub_rn((double)iy[gi], (double)pos.y);
+        const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        if (d2 < (double)cfg.robot_coll_dist) {
+          food_rew += (gi < cfg.n_food) ? 1.f : -1.f;
+          if (cfg.respawn) place_item(cfg, genv, STREAM_ITEM, (uint32_t)i0.z, gi, pos.x, pos.y, ix[gi], iy[gi]);
+          else { ix[gi] = 100.f; iy[gi] = 0.f; }
+        }
+      }
+    }
+    // observation: point_bot.py:48-67 (roll = pitch = yaw = 0) + sensor gather_base.py:118-168
+    float o[8 + 2 * HRL_MAX_BINS];
+    {
+      float sa, ca;
+      sincosf(atan2f(0.f - pos.y, 0.f - pos.x), &sa, &ca);
+      o[0] = pos.z - initial_z; o[1] = sa; o[2] = ca; o[3] = 0.3f * vel.x; o[4] = 0.3f * vel.y; o[5] = 0.3f * vel.z; o[6] = 0.f; o[7] = 0.f;
+      double best[2 * HRL_MAX_BINS];
+      for (int b = 0; b < 2 * nb; b++) best[b] = -1.0;
+      for (int gi = 0; gi < n_items; gi++) {
+        double d2;
+        const int b = gather_item_bin(pos.x, pos.y, 0.f, ix[gi], iy[gi], nb, cfg.sensor_range, cfg.sensor_span, &d2);
+        if (b >= 0) {
+          const int idx = (gi < cfg.n_food ? 0 : nb) + b;
+          if (best[idx] < 0.0 || d2 < best[idx]) best[idx] = d2;
+        }
+      }
+      for (int b = 0; b < 2 * nb; b++) o[8 + b] = best[b] < 0.0 ? 0.f : (float)(1.0 - best[b] / (double)cfg.sensor_range);
+    }
+    if (mode == 0 && pass == 0) {
+      bool fin = true;
+      for (int i = 0; i < 8; i++) fin = fin && isfinite(o[i]);
+      done = !fin;  // PointBot.alive_bonus is always 1 (point_bot.py:73-74)
+      i0.x++; i0.z++;
+      float trunc = 0.f;
+      if (cfg.max_episode_steps > 0 && i0.x >= cfg.max_episode_steps) { trunc = done ? 0.f : 1.f; done = 1; }
+      rew_out[e] = food_rew;
+      done_out[e] = (uint8_t)done;
+      if (info_out) reinterpret_cast<float4*>(info_out)[e] = make_float4(food_rew, 0.f, trunc, (float)i0.x);
+      if (done && cfg.auto_reset) {
+        if (term_out) for (int i = 0; i < D; i++) term_out[(size_t)e * D + i] = o[i];
+        do_reset = true;
+        continue;
+      }
+    }
+    if (emit && obs_out) for (int i = 0; i < D; i++) obs_out[(size_t)e * D + i] = o[i];
+    break;
+  }
+  st.base[e * 4 + 0] = make_float4(pos.x, pos.y, pos.z, initial_z);
+  st.base[e * 4 + 2] = make_float4(vel.x, vel.y, vel.z, 0.f);
+  st.misci[e * 2 + 0] = i0;
+#pragma unroll
+  for (int l = 0; l < 8; l++) st.items[e * 8 + l] = make_float4(ix[2 * l], iy[2 * l], ix[2 * l + 1], iy[2 * l + 1]);
+}
+
+// ------------------------------------------------------------------------------------------
+// state import / export (public layout of include/hrl_b200.h), one thread per env
+// ------------------------------------------------------------------------------------------
+__global__ void get_state_kernel(int N, DevState st, float* __restrict__ f, int32_t* __restrict__ iv) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  float* o = f + (size_t)e * HRL_STATE_F;
+  for (int i = 0; i < HRL_STATE_F; i++) o[i] = 0.f;
+  const float4 b0 = st.base[e * 4], b1 = st.base[e * 4 + 1], b2 = st.base[e * 4 + 2], b3 = st.base[e * 4 + 3];
+  o[HRL_SF_POS] = b0.x; o[HRL_SF_POS + 1] = b0.y; o[HRL_SF_POS + 2] = b0.z; o[HRL_SF_INITIAL_Z] = b0.w;
+  o[HRL_SF_QUAT] = b1.x; o[HRL_SF_QUAT + 1] = b1.y; o[HRL_SF_QUAT + 2] = b1.z; o[HRL_SF_QUAT + 3] = b1.w;
+  o[HRL_SF_LINVEL] = b2.x; o[HRL_SF_LINVEL + 1] = b2.y; o[HRL_SF_LINVEL + 2] = b2.z; o[HRL_SF_POTENTIAL] = b2.w;
+  o[HRL_SF_ANGVEL] = b3.x; o[HRL_SF_ANGVEL + 1] = b3.y; o[HRL_SF_ANGVEL + 2] = b3.z; o[HRL_SF_WTD] = b3.w;
+  for (int k = 0; k < 4; k++) {
+    const float4 l = st.leg[e * 4 + k];
+    o[HRL_SF_Q + 2 * k] = l.x; o[HRL_SF_Q + 2 * k + 1] = l.y; o[HRL_SF_QD + 2 * k] = l.z; o[HRL_SF_QD + 2 * k + 1] = l.w;
+  }
+  const float4 m0 = st.miscf[e * 2], m1 = st.miscf[e * 2 + 1];
+  o[HRL_SF_TARGET] = m0.x; o[HRL_SF_TARGET + 1] = m0.y;
+  o[HRL_SF_FEET] = m1.x; o[HRL_SF_FEET + 1] = m1.y; o[HRL_SF_FEET + 2] = m1.z; o[HRL_SF_FEET + 3] = m1.w;
+  for (int l = 0; l < 8; l++) {
+    const float4 a = st.items[e * 8 + l];
+    o[HRL_SF_ITEMS + 4 * l] = a.x; o[HRL_SF_ITEMS + 4 * l + 1] = a.y; o[HRL_SF_ITEMS + 4 * l + 2] = a.z; o[HRL_SF_ITEMS + 4 * l + 3] = a.w;
+  }
+  const int4 i0 = st.misci[e * 2], i1 = st.misci[e * 2 + 1];
+  int32_t* q = iv + (size_t)e * HRL_STATE_I;
+  for (int i = 0; i < HRL_STATE_I; i++) q[i] = 0;
+  q[HRL_SI_T] = i0.x; q[HRL_SI_EPISODE] = i0.y; q[HRL_SI_STEPS] = i0.z; q[HRL_SI_GOALS_LEFT] = i0.w;
+  q[HRL_SI_SINCE] = i1.x; q[HRL_SI_REWARDED] = i1.y;
+}
+
+__global__ void set_state_kernel(int N, DevState st, const float* __restrict__ f, const int32_t* __restrict__ iv) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  const float* o = f + (size_t)e * HRL_STATE_F;
+  st.base[e * 4] = make_float4(o[HRL_SF_POS], o[HRL_SF_POS + 1], o[HRL_SF_POS + 2], o[HRL_SF_INITIAL_Z]);
+  st.base[e * 4 + 1] = make_float4(o[HRL_SF_QUAT], o[HRL_SF_QUAT + 1], o[HRL_SF_QUAT + 2], o[HRL_SF_QUAT + 3]);
+  st.base[e * 4 + 2] = make_float4(o[HRL_SF_LINVEL], o[HRL_SF_LINVEL + 1], o[HRL_SF_LINVEL + 2], o[HRL_SF_POTENTIAL]);
+  st.base[e * 4 + 3] = make_float4(o[HRL_SF_ANGVEL], o[HRL_SF_ANGVEL + 1], o[HRL_SF_ANGVEL + 2], o[HRL_SF_WTD]);
+  for (int k = 0; k < 4; k++)
+    st.leg[e * 4 + k] = make_float4(o[HRL_SF_Q + 2 * k], o[HRL_SF_Q + 2 * k + 1], o[HRL_SF_QD + 2 * k], o[HRL_SF_QD + 2 * k + 1]);
+  st.miscf[e * 2] = make_float4(o[HRL_SF_TARGET], o[HRL_SF_TARGET + 1], 0.f, 0.f);
+  st.miscf[e * 2 + 1] = make_float4(o[HRL_SF_FEET], o[HRL_SF_FEET + 1], o[HRL_SF_FEET + 2], o[HRL_SF_FEET + 3]);
+  for (int l = 0; l < 8; l++)
+    st.items[e * 8 + l] = make_float4(o[HRL_SF_ITEMS + 4 * l], o[HRL_SF_ITEMS + 4 * l + 1], o[HRL_SF_ITEMS + 4 * l + 2], o[HRL_SF_ITEMS + 4 * l + 3]);
+  const int32_t* q = iv + (size_t)e * HRL_STATE_I;
+  st.misci[e * 2] = make_int4(q[HRL_SI_T], q[HRL_SI_EPISODE], q[HRL_SI_STEPS], q[HRL_SI_GOALS_LEFT]);
+  st.misci[e * 2 + 1] = make_int4(q[HRL_SI_SINCE], q[HRL_SI_REWARDED], 0, 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone parity kernels
+// ------------------------------------------------------------------------------------------
+__global__ void gather_sensor_kernel(int M, int n_bins, float range, float span, const float* __restrict__ xy,
+                                     const float* __restrict__ yaw, const float* __restrict__ items,
+                                     float* __restrict__ food, float* __restrict__ poison, int32_t* __restrict__ bins) {
+  // 16 lanes per case (one per item), 2 cases per warp
+  __shared__ unsigned long long sb[8][2][2 * HRL_MAX_BINS];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = tid >> 4, gi = tid & 15, warp = threadIdx.x >> 5, half = (threadIdx.x >> 4) & 1, lane16 = threadIdx.x & 15;
+  for (int i = lane16; i < 2 * HRL_MAX_BINS; i += 16) sb[warp][half][i] = 0x7ff0000000000000ull;
+  __syncwarp();
+  const bool ok = m < M;
+  int b = -1;
+  if (ok) {
+    double d2;
+    b = gather_item_bin(xy[2 * m], xy[2 * m + 1], yaw[m], items[(m * 16 + gi) * 2], items[(m * 16 + gi) * 2 + 1], n_bins, range, span, &d2);
+    if (bins) bins[m * 16 + gi] = b;
+    if (b >= 0) atomicMin(&sb[warp][half][(gi < 8 ? 0 : HRL_MAX_BINS) + b], (unsigned long long)__double_as_longlong(d2));
+  }
+  __syncwarp();
+  if (ok)
+    for (int i = lane16; i < 2 * n_bins; i += 16) {
+      const int ty = i / n_bins, bb = i - ty * n_bins;
+      const unsigned long long bits = sb[warp][half][ty * HRL_MAX_BINS + bb];
+      const float v = bits == 0x7ff0000000000000ull ? 0.f : (float)(1.0 - __longlong_as_double((long long)bits) / (double)range);
+      (ty ? poison : food)[m * n_bins + bb] = v;
+    }
+}
+
+__global__ void sense_walls_kernel(int M, int n_bins, float span, float range, int n_lines, const float* __restrict__ bounds,
+                                   const float* __restrict__ xy, const float* __restrict__ yaw, float* __restrict__ out) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= M * n_bins) return;
+  const int m = tid / n_bins, i = tid - m * n_bins;
+  out[tid] = lidar_ray(i, n_bins, span, range, n_lines, bounds, xy[2 * m], xy[2 * m + 1], yaw[m]);
+}
+
+// ------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------
+static int scene_bounds(const hrl_config* cfg, float* b) {
+  // sizeable_enclosed_scene.py:25-34 then maze_scene.py:15-21 (same order as the reference)
+  const float x1 = cfg->world_size[0] / 2.f, y1 = cfg->world_size[1] / 2.f, x2 = -x1, y2 = -y1;
+  const float w[4][4] = {{x1, y1, x2, y1}, {x1, y1, x1, y2}, {x2, y2, x2, y1}, {x2, y2, x1, y2}};
+  memcpy(b, w, sizeof w);
+  if (!cfg->has_box) return 4;
+  const float bx1 = cfg->box_hi[0], by1 = cfg->box_hi[1], bx2 = cfg->box_lo[0], by2 = cfg->box_lo[1];
+  const float bb[3][4] = {{bx1, by1, bx1, by2}, {bx2, by2, bx2, by1}, {bx2, by2, bx1, by2}};
+  memcpy(b + 16, bb, sizeof bb);
+  return 7;
+}
+
+extern "C" {
+
+const char* hrl_last_error(void) { return g_err; }
+const char* hrl_version(void) { return "hrl_b200 0.1 (sm_100a; 4 lanes/env; MAXC=" "4" ")"; }
+int64_t hrl_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int hrl_default_config(int32_t kind, int32_t num_envs, hrl_config* c) {
+  if (!c) return set_err(HRL_E_INVALID, "null config");
+  memset(c, 0, sizeof *c);
+  c->env_kind = kind; c->num_envs = num_envs; c->seed = 0; c->max_episode_steps = 2000; c->auto_reset = 1;
+  // third-party constants recalled in SURVEY.md App. A.2/A.3 [3P-MEM]
+  c->gravity = 9.8f; c->dt = 0.0165f; c->substeps = 4; c->solver_iters = 5;
+  c->contact_erp = 0.9f; c->limit_erp = 0.2f; c->lin_damping = 0.04f; c->ang_damping = 0.04f;
+  c->friction = 1.5f * 0.8f; c->limit_max_impulse = 100.f; c->max_coord_vel = 100.f; c->contact_margin = 0.02f;
+  c->torque_scale = 250.f; c->torque_first_substep_only = 1;
+  c->ground_z = 0.005f; c->has_walls = 1; c->has_box = 0;
+  // ant_gather_env.py:16-29
+  c->n_food = 8; c->n_poison = 8; c->n_bins = 10; c->sensor_range = 20.f; c->sensor_span = (float)HRL_PI_D;
+  c->robot_coll_dist = 1.f; c->robot_object_spacing = 2.f; c->dying_cost = -10.f; c->respawn = 1; c->use_sensor = 1;
+  // ant_maze_bullet_env.py:23-25
+  c->tol = 1.5f; c->done_at_target = 1; c->inner_rew_weight = 0.f; c->target_encoding = 0; c->sense_walls = 1;
+  // ant_flagrun_env.py:14-16,157-160
+  c->flag_max_targets = 100; c->flag_timeout = 200; c->flag_size = 10.f; c->goal_reach_rew = 5000.f; c->flag_seed = 123;
+  c->electricity_cost = -2.0f; c->stall_torque_cost = -0.1f; c->joints_at_limit_cost = -0.1f;
+  switch (kind) {
+    case HRL_ANT_GATHER:
+      c->world_size[0] = c->world_size[1] = 15; c->start_pos[2] = 0.75f; break;
+    case HRL_POINT_GATHER:  // point_gather_env.py:8-21, point_bot.py:12,29, player_cube.xml:8
+      c->world_size[0] = c->world_size[1] = 15; c->start_pos[2] = 0.5f; c->n_bins = 5;
+      c->friction = 0.1f * 0.8f; c->torque_scale = 500.f; break;
+    case HRL_ANT_MAZE:
+    case HRL_ANT_MAZE_MJ: {  // maze_scene.py:9-21, ant_maze_bullet_env.py:13-14,27; ant_maze_mj_env.py:13-14
+      c->world_size[0] = 10; c->world_size[1] = 18; c->has_box = 1;
+      c->box_lo[0] = -5; c->box_lo[1] = -2; c->box_lo[2] = 0; c->box_hi[0] = 1; c->box_hi[1] = 2; c->box_hi[2] = 2;
+      c->start_pos[0] = -2; c->start_pos[1] = -5; c->start_pos[2] = 0.25f;
+      c->sensor_range = 5.f; c->sensor_span = (float)(2 * HRL_PI_D);
+      c->n_scene_parts = 3; c->scene_parts_sum[0] = -7; c->scene_parts_sum[1] = 0;  // quirk Q1
+      if (kind == HRL_ANT_MAZE) {
+        const float t[4][2] = {{2, -3}, {2, 0}, {2, 3}, {-2, 4}};
+        c->n_targets = 4; memcpy(c->targets, t, sizeof t);
+      } else {
+        const float t[5][2] = {{2, -4}, {2, 0}, {2, 4}, {0, 4}, {-2, 4}};
+        c->n_targets = 5; memcpy(c->targets, t, sizeof t);
+      }
+    } break;
+    case HRL_ANT_FLAGRUN:  // ant_flagrun_env.py:14-16,62,133-135,142
+      c->world_size[0] = c->world_size[1] = 12; c->start_pos[2] = 0.25f; c->tol = 0.5f;
+      c->n_scene_parts = 2; c->scene_parts_sum[0] = -6; c->scene_parts_sum[1] = 0;
+      c->electricity_cost = 0; c->stall_torque_cost = 0; c->joints_at_limit_cost = 0;
+      break;
+    case HRL_ANT_MJ:  // envs/MjAnt.py:31 on the pybulletgym stadium ground
+      c->world_size[0] = c->world_size[1] = 50; c->has_walls = 0; c->ground_z = 0.f; c->start_pos[2] = 0.75f; break;
+    default: return set_err(HRL_E_INVALID, "unknown env_kind");
+  }
+  return HRL_OK;
+}
+
+int hrl_obs_dim(const hrl_config* c) {
+  if (!c) return -1;
+  switch (c->env_kind) {
+    case HRL_ANT_GATHER: return 26 + 2 * c->n_bins;                     // ant_gather_env.py:54-55
+    case HRL_ANT_MAZE: return 26 + 2 + (c->sense_walls ? c->n_bins : 0);  // ant_maze_bullet_env.py:54-57
+    case HRL_ANT_FLAGRUN: return 28;
+    case HRL_ANT_MJ: return 29;                                          // MjAnt.py:15
+    case HRL_ANT_MAZE_MJ: return 29 + 3 * c->n_bins + 1;                 // ant_maze_mj_env.py:50
+    case HRL_POINT_GATHER: return 8 + 2 * c->n_bins;                     // gather_base.py:54-55
+  }
+  return -1;
+}
+int hrl_act_dim(const hrl_config* c) { return !c ? -1 : (c->env_kind == HRL_POINT_GATHER ? 2 : 8); }
+
+static int validate(const hrl_config* c) {
+  if (!c) return set_err(HRL_E_INVALID, "null config");
+  if (c->num_envs <= 0) return set_err(HRL_E_INVALID, "num_envs must be > 0");
+  if (hrl_obs_dim(c) < 0) return set_err(HRL_E_INVALID, "unknown env_kind");
+  if (hrl_obs_dim(c) > HRL_OBS_STAGE) return set_err(HRL_E_INVALID, "observation wider than 64");
+  if (c->n_bins < 1 || c->n_bins > HRL_MAX_BINS) return set_err(HRL_E_INVALID, "n_bins out of range");
+  if (c->n_food < 0 || c->n_food > 8 || c->n_poison < 0 || c->n_poison > 8) return set_err(HRL_E_INVALID, "n_food/n_poison out of range");
+  if (c->substeps < 1 || c->solver_iters < 0) return set_err(HRL_E_INVALID, "bad substeps/solver_iters");
+  if (c->n_targets > HRL_MAX_TARGETS || c->flag_max_targets > 127) return set_err(HRL_E_INVALID, "too many targets");
+  if ((c->env_kind == HRL_ANT_MAZE || c->env_kind == HRL_ANT_MAZE_MJ) && c->n_targets < 1) return set_err(HRL_E_INVALID, "maze needs targets");
+  return HRL_OK;
+}
+
+int hrl_destroy(hrl_handle* h) {
+  if (!h) return HRL_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->st.base); cudaFree(h->st.leg); cudaFree(h->st.items); cudaFree(h->st.miscf); cudaFree(h->st.misci);
+  cudaFree(h->st.stats); cudaFree(h->d_bounds);
+  cudaFree(h->s_act); cudaFree(h->s_obs); cudaFree(h->s_rew); cudaFree(h->s_info); cudaFree(h->s_done);
+  delete h;
+  return HRL_OK;
+}
+
+int hrl_create(const hrl_config* cfg, int32_t device, hrl_handle** out) {
+  if (!out) return set_err(HRL_E_INVALID, "null out");
+  *out = nullptr;
+  int rc = validate(cfg);
+  if (rc) return rc;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) return set_err(HRL_E_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return set_err(HRL_E_INVALID, "bad device index");
+  CK(cudaSetDevice(device));
+  hrl_handle* h = new hrl_handle();
+  memset(h, 0, sizeof *h);
+  h->cfg = *cfg; h->device = device; h->N = cfg->num_envs; h->D = hrl_obs_dim(cfg); h->A = hrl_act_dim(cfg);
+  const size_t N = (size_t)h->N;
+#define ALLOC(p, bytes)                                                   \
+  do {                                                                    \
+    cudaError_t _e = cudaMalloc((void**)&(p), (bytes));                   \
+    if (_e != cudaSuccess) { hrl_destroy(h); return cuda_fail(_e, "cudaMalloc"); } \
+    cudaMemset((p), 0, (bytes));                                          \
+  } while (0)
+  ALLOC(h->st.base, N * 4 * sizeof(float4));
+  ALLOC(h->st.leg, N * 4 * sizeof(float4));
+  ALLOC(h->st.items, N * 8 * sizeof(float4));
+  ALLOC(h->st.miscf, N * 2 * sizeof(float4));
+  ALLOC(h->st.misci, N * 2 * sizeof(int4));
+  ALLOC(h->st.stats, 4 * sizeof(unsigned long long));
+  ALLOC(h->d_bounds, 7 * 4 * sizeof(float));
+  ALLOC(h->s_act, N * h->A * sizeof(float));
+  ALLOC(h->s_obs, N * h->D * sizeof(float));
+  ALLOC(h->s_rew, N * sizeof(float));
+  ALLOC(h->s_info, N * 4 * sizeof(float));
+  ALLOC(h->s_done, N);
+#undef ALLOC
+  float b[28];
+  h->n_lines = scene_bounds(cfg, b);
+  CK(cudaMemcpy(h->d_bounds, b, sizeof b, cudaMemcpyHostToDevice));
+  // opt in to the dynamic shared memory the ant kernels need
+  const int smem = HRL_WARPS_PER_CTA * SMEM_PER_WARP_FLOATS * (int)sizeof(float);
+  CK(cudaFuncSetAttribute(ant_env_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(ant_env_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  *out = h;
+  // identity quaternions so that an un-reset handle is still a valid state
+  rc = hrl_reset(h, nullptr, nullptr, nullptr);
+  if (rc) { hrl_destroy(h); *out = nullptr; return rc; }
+  CK(cudaDeviceSynchronize());
+  return HRL_OK;
+}
+
+static int launch_env(hrl_handle* h, int mode, int n_sub, const float* act, const uint8_t* mask, float* obs, float* rew,
+                      uint8_t* done, float* info, float* term, cudaStream_t s) {
+  CK(cudaSetDevice(h->device));
+  if (h->cfg.env_kind == HRL_POINT_GATHER) {
+    const int B = 128, G = (h->N + B - 1) / B;
+    point_env_kernel<<<G, B, 0, s>>>(h->cfg, h->st, act, mask, obs, rew, done, info, term, mode, n_sub, h->D);
+  } else {
+    const int T = 32 * HRL_WARPS_PER_CTA, G = (h->N * 4 + T - 1) / T;
+    const size_t smem = (size_t)HRL_WARPS_PER_CTA * SMEM_PER_WARP_FLOATS * sizeof(float);
+    if (h->cfg.env_kind == HRL_ANT_GATHER)
+      ant_env_kernel<0><<<G, T, smem, s>>>(h->cfg, h->st, h->d_bounds, h->n_lines, act, mask, obs, rew, done, info, term, mode, n_sub, h->D);
+    else
+      ant_env_kernel<1><<<G, T, smem, s>>>(h->cfg, h->st, h->d_bounds, h->n_lines, act, mask, obs, rew, done, info, term, mode, n_sub, h->D);
+  }
+  g_launches++;
+  CK(cudaGetLastError());
+  return HRL_OK;
+}
+
+int hrl_reset(hrl_handle* h, const uint8_t* d_mask, float* d_obs, void* stream) {
+  if (!h) return set_err(HRL_E_INVALID, "null handle");
+  return launch_env(h, 2, 0, nullptr, d_mask, d_obs, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int hrl_step(hrl_handle* h, const float* d_actions, float* d_obs, float* d_rew, uint8_t* d_done, float* d_info,
+             float* d_terminal_obs, void* stream) {
+  if (!h || !d_actions || !d_obs || !d_rew || !d_done) return set_err(HRL_E_INVALID, "null argument to hrl_step");
+  return launch_env(h, 0, 0, d_actions, nullptr, d_obs, d_rew, d_done, d_info, d_terminal_obs, (cudaStream_t)stream);
+}
+
+int hrl_step_host(hrl_handle* h, const float* h_actions, float* h_obs, float* h_rew, uint8_t* h_done, float* h_info,
+                  void* stream) {
+  if (!h || !h_actions || !h_obs || !h_rew || !h_done) return set_err(HRL_E_INVALID, "null argument to hrl_step_host");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  const size_t N = (size_t)h->N;
+  CK(cudaMemcpyAsync(h->s_act, h_actions, N * h->A * sizeof(float), cudaMemcpyHostToDevice, s));
+  int rc = launch_env(h, 0, 0, h->s_act, nullptr, h->s_obs, h->s_rew, h->s_done, h_info ? h->s_info : nullptr, nullptr, s);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h_obs, h->s_obs, N * h->D * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h_rew, h->s_rew, N * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h_done, h->s_done, N, cudaMemcpyDeviceToHost, s));
+  if (h_info) CK(cudaMemcpyAsync(h_info, h->s_info, N * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return HRL_OK;
+}
+
+int hrl_observe(hrl_handle* h, float* d_obs, void* stream) {
+  if (!h || !d_obs) return set_err(HRL_E_INVALID, "null argument to hrl_observe");
+  return launch_env(h, 3, 0, nullptr, nullptr, d_obs, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int hrl_substeps(hrl_handle* h, const float* d_actions, int32_t n_sub, void* stream) {
+  if (!h || !d_actions || n_sub < 0) return set_err(HRL_E_INVALID, "bad argument to hrl_substeps");
+  return launch_env(h, 1, n_sub, d_actions, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int hrl_get_state(hrl_handle* h, float* d_f, int32_t* d_i, void* stream) {
+  if (!h || !d_f || !d_i) return set_err(HRL_E_INVALID, "null argument to hrl_get_state");
+  CK(cudaSetDevice(h->device));
+  get_state_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->N, h->st, d_f, d_i);
+  g_launches++;
+  CK(cudaGetLastError());
+  return HRL_OK;
+}
+int hrl_set_state(hrl_handle* h, const float* d_f, const int32_t* d_i, void* stream) {
+  if (!h || !d_f || !d_i) return set_err(HRL_E_INVALID, "null argument to hrl_set_state");
+  CK(cudaSetDevice(h->device));
+  set_state_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->N, h->st, d_f, d_i);
+  g_launches++;
+  CK(cudaGetLastError());
+  return HRL_OK;
+}
+
+int hrl_gather_sensor(int32_t M, int32_t n_bins, float sensor_range, float sensor_span, const float* d_xy,
+                      const float* d_yaw, const float* d_items, float* d_food, float* d_poison, int32_t* d_bins,
+                      void* stream) {
+  if (M < 0 || n_bins < 1 || n_bins > HRL_MAX_BINS || !d_xy || !d_yaw || !d_items || !d_food || !d_poison)
+    return set_err(HRL_E_INVALID, "bad argument to hrl_gather_sensor");
+  if (M == 0) return HRL_OK;
+  const int T = 256, G = (M * 16 + T - 1) / T;
+  gather_sensor_kernel<<<G, T, 0, (cudaStream_t)stream>>>(M, n_bins, sensor_range, sensor_span, d_xy, d_yaw, d_items, d_food, d_poison, d_bins);
+  g_launches++;
+  CK(cudaGetLastError());
+  return HRL_OK;
+}
+
+int hrl_sense_walls(int32_t M, int32_t n_bins, float span, float range, int32_t n_lines, const float* d_bounds,
+                    const float* d_xy, const float* d_yaw, float* d_out, void* stream) {
+  if (M < 0 || n_bins < 1 || n_lines < 0 || !d_bounds || !d_xy || !d_yaw || !d_out)
+    return set_err(HRL_E_INVALID, "bad argument to hrl_sense_walls");
+  if (M == 0) return HRL_OK;
+  const int T = 128, G = (M * n_bins + T - 1) / T;
+  sense_walls_kernel<<<G, T, 0, (cudaStream_t)stream>>>(M, n_bins, span, range, n_lines, d_bounds, d_xy, d_yaw, d_out);
+  g_launches++;
+  CK(cudaGetLastError());
+  return HRL_OK;
+}
+
+/* instrumentation for the FLOP model (bench.py roofline): contacts, limit rows, env-substeps */
+int hrl_get_stats(hrl_handle* h, unsigned long long out[4], int reset) {
+  if (!h || !out) return set_err(HRL_E_INVALID, "null argument to hrl_get_stats");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(out, h->st.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) CK(cudaMemset(h->st.stats, 0, 4 * sizeof(unsigned long long)));
+  return HRL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+// hrl_sensors.cuh - task-layer sensors shared by the fused step kernels and the stand-alone
+// parity kernels.  Citations relative to /root/reference/hrl_pybullet_envs.
+#pragma once
+#include "hrl_math.cuh"
+
+#define HRL_PI_D 3.14159265358979323846
+#define HRL_PI_F 3.14159265358979323846f
+
+// The config carries spans as float32; the reference's defaults are the float64 constants pi
+// and 2*pi (ant_gather_env.py:22, ant_maze_bullet_env.py:23), so those two are snapped back.
+__host__ __device__ __forceinline__ double snap_span(float s) {
+  if (s == (float)(2.0 * HRL_PI_D)) return 2.0 * HRL_PI_D;
+  if (s == (float)HRL_PI_D) return HRL_PI_D;
+  return (double)s;
+}
+
+// Gather sector sensor for ONE item (envs/gather/ant_gather_env.py:143-162, twin
+// gather_base.py:134-152).  Returns the bin or -1; *d2_out = squared xy distance in double
+// (ant_gather_env.py:198-200), identical bit-for-bit to the reference's float64 value for
+// float32-representable inputs (explicit _rn ops: no FMA contraction).
+// Angle/bin: float32 fast path; when the float result is within 2e-4 of any decision
+// boundary (bin edge, +-half span) the reference's exact float64 sequence is evaluated
+// instead, which makes the bin index bit-exact (SURVEY.md hard part 5).
+__device__ __forceinline__ int gather_item_bin(float rx, float ry, float yaw, float ox, float oy, int n_bins,
+                                               float sensor_range, float span, double* d2_out) {
+  double dxd = __dsub_rn((double)ox, (double)rx), dyd = __dsub_rn((double)oy, (double)ry);
+  double d2 = __dadd_rn(__dmul_rn(dxd, dxd), __dmul_rn(dyd, dyd));
+  *d2_out = d2;
+  if (d2 > (double)sensor_range) return -1;  // :145 (squared distance vs unsquared range, kept)
+  float dx = (float)dxd, dy = (float)dyd;
+  const float two_pi = 2.0f * HRL_PI_F;
+  float a = atan2f(dy, dx) - yaw;  // :148
+  a = fmodf(a, two_pi);
+  if (a < 0.f) a += two_pi;  // Python % semantics :151
+  if (a > HRL_PI_F) a -= two_pi;
+  float half = 0.5f * span, res = span / (float)n_bins;
+  float t = (a + half) / res;
+  bool risky = fabsf(fabsf(a) - half) < 2e-4f || fabsf(t - rintf(t)) < 2e-4f || !(fabsf(a) < 1e30f);
+  if (!risky) {
+    if (fabsf(a) > half) return -1;  // :159
+    int b = (int)t;                  // :161
+    return b > n_bins - 1 ? n_bins - 1 : b;
+  }
+  // exact path: the reference's float64 expression sequence
+  double ad = atan2(dyd, dxd) - (double)yaw;
+  ad = fmod(ad, 2.0 * HRL_PI_D);
+  if (ad < 0.0) ad += 2.0 * HRL_PI_D;
+  if (ad > HRL_PI_D) ad -= 2.0 * HRL_PI_D;
+  if (ad < -HRL_PI_D) ad += 2.0 * HRL_PI_D;
+  double spand = snap_span(span);
+  double halfd = spand * 0.5, resd = spand / (double)n_bins;
+  if (fabs(ad) > halfd) return -1;
+  int b = (int)((ad + halfd) / resd);
+  // the reference raises IndexError at exactly +half span; clamp instead
+  return b > n_bins - 1 ? n_bins - 1 : b;
+}
+
+// intersection_utils.py:93-104 (tie order 1,4,2,3)
+__device__ __forceinline__ int quadrant_d(double x, double y) {
+  if (x >= 0 && y >= 0) return 1;
+  if (x >= 0 && y <= 0) return 4;
+  if (x <= 0 && y >= 0) return 2;
+  if (x <= 0 && y <= 0) return 3;
+  return 0;
+}
+
+// One ray of the wall lidar, sizeable_enclosed_scene.py:63-97, evaluated in float64 with the
+// reference's determinant formula (intersection_utils.py:84-90); ray and bounds are infinite
+// lines.  bounds: n_lines x (x1,y1,x2,y2).
+__device__ __forceinline__ float lidar_ray(int i, int n_bins, float span_f, float range_f, int n_lines,
+                                           const float* __restrict__ bounds, float pxf, float pyf, float yawf) {
+  const double span = snap_span(span_f), range = (double)range_f, px = (double)pxf, py = (double)pyf, yaw = (double)yawf;
+  double ang;
+  if (span == 2.0 * HRL_PI_D) ang = HRL_PI_D / 2 + yaw + ((double)(i + 1) / (double)n_bins) * span;  // :68-69
+  else ang = HRL_PI_D / 2 + yaw + ((double)i / (double)(n_bins - 1)) * span;                           // :70-71
+  double sn, cs;
+  sincos(ang, &sn, &cs);
+  double x2 = __dadd_rn(px, __dmul_rn(range, cs)), y2 = __dadd_rn(py, __dmul_rn(range, sn));
+  int sq = quadrant_d(__dsub_rn(x2, px), __dsub_rn(y2, py));
+  double best = 0.0;
+  for (int l = 0; l < n_lines; l++) {
+    double x3 = bounds[4 * l], y3 = bounds[4 * l + 1], x4 = bounds[4 * l + 2], y4 = bounds[4 * l + 3];
+    double x12 = __dsub_rn(px, x2), y12 = __dsub_rn(py, y2), x34 = __dsub_rn(x3, x4), y34 = __dsub_rn(y3, y4);
+    double d = __dsub_rn(__dmul_rn(x12, y34), __dmul_rn(y12, x34));
+    if (d == 0.0) continue;
+    double c12 = __dsub_rn(__dmul_rn(px, y2), __dmul_rn(py, x2));
+    double c34 = __dsub_rn(__dmul_rn(x3, y4), __dmul_rn(y3, x4));
+    double ix = __ddiv_rn(__dsub_rn(__dmul_rn(c12, x34), __dmul_rn(x12, c34)), d);
+    double iy = __ddiv_rn(__dsub_rn(__dmul_rn(c12, y34), __dmul_rn(y12, c34)), d);
+    double ddx = __dsub_rn(px, ix), ddy = __dsub_rn(py, iy);
+    double dist = sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
+    if (dist > range) continue;
+    if (sq != quadrant_d(__dsub_rn(ix, px), __dsub_rn(iy, py))) continue;
+    double val = 1.0 - dist / range;
+    if (val > best) best = val;
+  }
+  return (float)best;
+}
+
+// Bullet getEulerFromQuaternion (SURVEY.md A.3 "Queries")
+__device__ __forceinline__ void quat_to_rpy(float x, float y, float z, float w, float& roll, float& pitch, float& yaw) {
+  float sarg = -2.f * (x * z - w * y);
+  if (sarg <= -0.99999f) { pitch = -0.5f * HRL_PI_F; roll = 0.f; yaw = 2.f * atan2f(x, -y); }
+  else if (sarg >= 0.99999f) { pitch = 0.5f * HRL_PI_F; roll = 0.f; yaw = 2.f * atan2f(-x, y); }
+  else {
+    pitch = asinf(sarg);
+    roll = atan2f(2.f * (y * z + w * x), w * w - x * x - y * y + z * z);
+    yaw = atan2f(2.f * (x * y + w * z), w * w + x * x - y * y - z * z);
+  }
+}

@@ -1,0 +1,113 @@
+"""Minimal gym<=0.21 surface (gym itself is not installed in this image): ``Box``, ``register``,
+``make`` and a single-env view over ``VecEnv`` so that the reference README loop
+(README.md:20-37) runs unchanged apart from the import.
+
+Registered ids = hrl_pybullet_envs/__init__.py:9-16 plus ``AntMjBulletEnv-v0`` (README.md:13).
+If a real ``gym`` / ``gymnasium`` is importable the ids are registered there as well.
+"""
+import numpy as np
+
+from .config import ENV_IDS, HRL_POINT_GATHER
+
+
+class Box:
+    def __init__(self, low, high, shape, dtype=np.float32):
+        self.low = np.full(shape, low, dtype=dtype)
+        self.high = np.full(shape, high, dtype=dtype)
+        self.shape = tuple(shape)
+        self.dtype = np.dtype(dtype)
+        self._rng = np.random.RandomState()
+
+    def seed(self, seed=None):
+        self._rng = np.random.RandomState(seed)
+
+    def sample(self):
+        lo = np.where(np.isfinite(self.low), self.low, -1.0)
+        hi = np.where(np.isfinite(self.high), self.high, 1.0)
+        return self._rng.uniform(lo, hi).astype(self.dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+    def __repr__(self):
+        return "Box(%s, %s, %s, %s)" % (self.low.min(), self.high.max(), self.shape, self.dtype)
+
+
+class SingleEnv:
+    """N=1 view: ``reset() -> obs``, ``step(a) -> (obs, rew, done, info)`` with numpy values.
+    Like gym's TimeLimit wrapper it does not auto-reset."""
+
+    metadata = {"render.modes": []}
+
+    def __init__(self, env_id, device=0, seed=0, **kwargs):
+        from .vec_env import VecEnv
+        self.vec = VecEnv(env_id, 1, device=device, seed=seed, auto_reset=False, **kwargs)
+        self.observation_space = Box(-np.inf, np.inf, (self.vec.D,))
+        self.action_space = Box(-1.0, 1.0, (self.vec.A,))
+        self.spec = type("Spec", (), {"id": env_id, "max_episode_steps": 2000})()
+        self._seed = seed
+        self._kwargs = kwargs
+
+    def seed(self, seed=None):
+        if seed is not None and seed != self._seed:
+            from .vec_env import VecEnv
+            self.vec.close()
+            self.vec = VecEnv(self.spec.id, 1, device=self.vec.device.index, seed=seed, auto_reset=False, **self._kwargs)
+            self._seed = seed
+        return [self._seed]
+
+    def reset(self):
+        return self.vec.reset().cpu().numpy()[0].copy()
+
+    def step(self, a):
+        import torch
+        act = torch.as_tensor(np.asarray(a, dtype=np.float32).reshape(1, -1), device=self.vec.device)
+        obs, rew, done, info = self.vec.step(act)
+        i = {k: (v[0].item() if v.ndim == 1 else v[0].cpu().numpy()) for k, v in info.items()}
+        if not i.pop("TimeLimit.truncated"):
+            pass
+        else:
+            i["TimeLimit.truncated"] = True
+        return obs.cpu().numpy()[0].copy(), float(rew[0].item()), bool(done[0].item()), i
+
+    def render(self, *a, **k):
+        return None  # headless batched simulator: no renderer
+
+    def close(self):
+        self.vec.close()
+
+
+registry = {}
+
+
+def register(id, entry_point=None, max_episode_steps=2000, **kw):
+    registry[id] = dict(entry_point=entry_point, max_episode_steps=max_episode_steps, **kw)
+
+
+def make(id, **kwargs):
+    if id not in registry:
+        raise KeyError("No registered env with id: %s" % id)
+    return SingleEnv(id, **kwargs)
+
+
+for _id in ENV_IDS:
+    register(_id, entry_point="hrl_pybullet_envs_b200.gym_shim:SingleEnv", max_episode_steps=2000)
+
+
+def register_with_installed_gym():
+    """Best effort: expose the ids through a real gym/gymnasium when one is importable."""
+    done = []
+    for modname in ("gym", "gymnasium"):
+        try:
+            mod = __import__(modname)
+            for _id in ENV_IDS:
+                try:
+                    mod.envs.registration.register(id=_id, entry_point=lambda _id=_id, **kw: SingleEnv(_id, **kw),
+                                                   max_episode_steps=2000)
+                except Exception:
+                    pass
+            done.append(modname)
+        except ImportError:
+            pass
+    return done

@@ -1,0 +1,190 @@
+"""Vectorised env: ``step(actions[N, A]) -> (obs[N, D], rew[N], done[N], info)`` as torch tensors.
+
+Host-side mirror of the reference's gym surface for N envs at once.  All arithmetic happens in
+the sm_100a kernels behind the C-ABI (``_cabi``); torch only supplies device memory and streams.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .config import (ENV_IDS, HRL_STATE_F, HRL_STATE_I, HRL_ANT_FLAGRUN, HRL_ANT_GATHER, HRL_POINT_GATHER, apply_kwargs)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class VecEnv:
+    """N independent envs of one reference id on one GPU.
+
+    Parameters mirror ``gym.make(id, **kwargs)`` of the reference plus ``num_envs``, ``device``,
+    ``seed`` and ``env_index_offset`` (global index of env 0, for multi-GPU shards).
+    """
+
+    def __init__(self, env_id, num_envs, device=0, seed=0, env_index_offset=0, auto_reset=True,
+                 max_episode_steps=2000, config_overrides=None, **kwargs):
+        if env_id not in ENV_IDS:
+            raise KeyError("unknown env id %r; known: %s" % (env_id, sorted(ENV_IDS)))
+        if not torch.cuda.is_available():
+            raise _cabi.HrlError("no CUDA device: hrl_pybullet_envs_b200 has no CPU fallback")
+        self.env_id = env_id
+        self.kind = ENV_IDS[env_id]
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        cfg = _cabi.default_config(self.kind, num_envs)
+        apply_kwargs(cfg, self.kind, kwargs)
+        if self.kind not in (HRL_ANT_FLAGRUN,) and "seed" not in kwargs:
+            cfg.seed = int(seed)
+        elif self.kind == HRL_ANT_FLAGRUN:
+            cfg.seed = int(seed)  # Flagrun's `seed` kwarg feeds the shared goal stream (flag_seed)
+        cfg.env_index_offset = int(env_index_offset)
+        cfg.auto_reset = int(bool(auto_reset))
+        cfg.max_episode_steps = int(max_episode_steps)
+        for k, v in (config_overrides or {}).items():
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self.L = _cabi.lib()
+        self.h = C.c_void_p()
+        _cabi.check(self.L.hrl_create(C.byref(cfg), self.device.index, C.byref(self.h)))
+        self.num_envs = self.N = num_envs
+        self.obs_dim = self.D = self.L.hrl_obs_dim(C.byref(cfg))
+        self.act_dim = self.A = self.L.hrl_act_dim(C.byref(cfg))
+        d = self.device
+        self._obs = torch.zeros(self.N, self.D, device=d)
+        self._rew = torch.zeros(self.N, device=d)
+        self._done = torch.zeros(self.N, dtype=torch.uint8, device=d)
+        self._info = torch.zeros(self.N, 4, device=d)
+        self._term = None
+        self._host = None
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.hrl_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ gym-like API
+    def seed(self, seed=None):
+        """Re-seeding happens at construction (counter RNG keyed by (seed, env index))."""
+        return [self.cfg.seed]
+
+    def reset(self, mask=None):
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        _cabi.check(self.L.hrl_reset(self.h, _ptr(m), _ptr(self._obs), self._stream()))
+        return self._obs
+
+    def step(self, actions, want_terminal_obs=False):
+        """actions: float32 CUDA tensor [N, A] (device path) or numpy array (host path)."""
+        if isinstance(actions, np.ndarray):
+            return self.step_host(actions)
+        a = actions
+        if a.dtype != torch.float32 or not a.is_contiguous() or a.device != self.device:
+            a = a.to(device=self.device, dtype=torch.float32).contiguous()
+        if a.numel() != self.N * self.A:
+            raise ValueError("actions must have shape (%d, %d)" % (self.N, self.A))
+        term = None
+        if want_terminal_obs:
+            if self._term is None:
+                self._term = torch.zeros(self.N, self.D, device=self.device)
+            term = self._term
+        _cabi.check(self.L.hrl_step(self.h, _ptr(a), _ptr(self._obs), _ptr(self._rew), _ptr(self._done),
+                                    _ptr(self._info), _ptr(term), self._stream()))
+        return self._obs, self._rew, self._done.bool(), self._info_dict(self._info, term)
+
+    def _info_dict(self, info, term=None):
+        d = {"TimeLimit.truncated": info[:, 2] > 0, "episode_length": info[:, 3]}
+        if self.kind in (HRL_ANT_GATHER, HRL_POINT_GATHER):
+            d["food_rew"] = info[:, 0]   # ant_gather_env.py:119
+            d["dead_rew"] = info[:, 1]
+        else:
+            d["inner_rew"] = info[:, 0]
+            if self.kind == HRL_ANT_FLAGRUN:
+                d["goals_left"] = info[:, 1]
+        if term is not None:
+            d["terminal_obs"] = term
+        return d
+
+    def step_host(self, actions):
+        """numpy in / numpy out through ``hrl_step_host`` (H2D + kernel + D2H + sync)."""
+        if self._host is None:
+            pin = torch.cuda.is_available()
+            self._host = dict(act=torch.zeros(self.N, self.A, pin_memory=pin), obs=torch.zeros(self.N, self.D, pin_memory=pin),
+                              rew=torch.zeros(self.N, pin_memory=pin), done=torch.zeros(self.N, dtype=torch.uint8, pin_memory=pin),
+                              info=torch.zeros(self.N, 4, pin_memory=pin))
+        H = self._host
+        H["act"].numpy()[...] = np.asarray(actions, dtype=np.float32).reshape(self.N, self.A)
+        _cabi.check(self.L.hrl_step_host(self.h, _ptr(H["act"]), _ptr(H["obs"]), _ptr(H["rew"]), _ptr(H["done"]),
+                                         _ptr(H["info"]), self._stream()))
+        info = H["info"].numpy()
+        d = {"TimeLimit.truncated": info[:, 2] > 0, "episode_length": info[:, 3]}
+        return H["obs"].numpy(), H["rew"].numpy(), H["done"].numpy().astype(bool), d
+
+    def observe(self):
+        _cabi.check(self.L.hrl_observe(self.h, _ptr(self._obs), self._stream()))
+        return self._obs
+
+    def substeps(self, actions, n_sub):
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        _cabi.check(self.L.hrl_substeps(self.h, _ptr(a), int(n_sub), self._stream()))
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def get_state(self):
+        f = torch.zeros(self.N, HRL_STATE_F, device=self.device)
+        i = torch.zeros(self.N, HRL_STATE_I, dtype=torch.int32, device=self.device)
+        _cabi.check(self.L.hrl_get_state(self.h, _ptr(f), _ptr(i), self._stream()))
+        return f, i
+
+    def set_state(self, f, i):
+        f = torch.as_tensor(f).to(device=self.device, dtype=torch.float32).contiguous()
+        i = torch.as_tensor(i).to(device=self.device, dtype=torch.int32).contiguous()
+        if f.shape != (self.N, HRL_STATE_F) or i.shape != (self.N, HRL_STATE_I):
+            raise ValueError("state tensors must be [N,%d] f32 and [N,%d] i32" % (HRL_STATE_F, HRL_STATE_I))
+        _cabi.check(self.L.hrl_set_state(self.h, _ptr(f), _ptr(i), self._stream()))
+
+    def stats(self, reset=True):
+        """In-kernel counters feeding the FLOP model: mean contacts / limit rows per env-substep."""
+        out = (C.c_ulonglong * 4)()
+        _cabi.check(self.L.hrl_get_stats(self.h, out, int(reset)))
+        n = max(int(out[2]), 1)
+        return {"contacts_per_substep": out[0] / n, "limit_rows_per_substep": out[1] / n, "env_substeps": int(out[2])}
+
+
+# ---- stand-alone sensors (parity entry points) ------------------------------------------
+def gather_sensor(xy, yaw, items, n_bins=10, sensor_range=20.0, sensor_span=np.pi):
+    """ant_gather_env.py:128-177 for M poses: returns (food[M,n], poison[M,n], bins[M,16])."""
+    L = _cabi.lib()
+    dev = xy.device
+    M = xy.shape[0]
+    xy = xy.to(torch.float32).contiguous(); yaw = yaw.to(torch.float32).contiguous()
+    items = items.to(torch.float32).contiguous()
+    food = torch.zeros(M, n_bins, device=dev); poison = torch.zeros(M, n_bins, device=dev)
+    bins = torch.full((M, 16), -1, dtype=torch.int32, device=dev)
+    _cabi.check(L.hrl_gather_sensor(M, n_bins, float(sensor_range), float(sensor_span), _ptr(xy), _ptr(yaw), _ptr(items),
+                                    _ptr(food), _ptr(poison), _ptr(bins),
+                                    C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return food, poison, bins
+
+
+def sense_walls(xy, yaw, bounds, n_bins=10, span=2 * np.pi, rng=5.0):
+    """sizeable_enclosed_scene.py:63-97 for M poses: returns out[M, n_bins]."""
+    L = _cabi.lib()
+    dev = xy.device
+    M = xy.shape[0]
+    xy = xy.to(torch.float32).contiguous(); yaw = yaw.to(torch.float32).contiguous()
+    bounds = bounds.to(device=dev, dtype=torch.float32).contiguous()
+    out = torch.zeros(M, n_bins, device=dev)
+    _cabi.check(L.hrl_sense_walls(M, n_bins, float(span), float(rng), bounds.shape[0], _ptr(bounds), _ptr(xy), _ptr(yaw),
+                                  _ptr(out), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out

@@ -64,12 +64,10 @@ enum {
 enum {
   HRL_SI_T = 0,          /* steps taken in this episode (TimeLimit counter)          */
   HRL_SI_EPISODE = 1,    /* number of resets so far                                  */
-  HRL_SI_RNG_ITEM = 2,   /* draw counter of the item-placement stream                */
-  HRL_SI_RNG_JOINT = 3,  /* draw counter of the joint-noise stream                   */
-  HRL_SI_RNG_GOAL = 4,   /* draw counter of the maze goal stream                     */
-  HRL_SI_GOALS_LEFT = 5, /* Flagrun: goals still in the list                         */
-  HRL_SI_SINCE = 6,      /* Flagrun: steps_since_goal_change (survives reset)        */
-  HRL_SI_REWARDED = 7    /* Flagrun: _rewarded                                       */
+  HRL_SI_STEPS = 2,      /* steps taken since creation (RNG draw index of respawns)  */
+  HRL_SI_GOALS_LEFT = 3, /* Flagrun: goals still in the list                         */
+  HRL_SI_SINCE = 4,      /* Flagrun: steps_since_goal_change (survives reset)        */
+  HRL_SI_REWARDED = 5    /* Flagrun: _rewarded; 6,7 spare                            */
 };
 
 /* ---- configuration: the reference's ctor kwargs + the recalled third-party constants --- */

