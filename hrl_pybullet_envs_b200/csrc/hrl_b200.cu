@@ -169,11 +169,12 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       const bool on = (i == 0) || !cfg.torque_first_substep_only;
       ant_substep(s, P, lc, on ? tau1 : 0.f, on ? tau2 : 0.f, rows, cands, lane, k, feet_ground, sc, sl);
     }
-    if (st.stats && active) {
-      sc = __reduce_add_sync(HRL_FULL_MASK, sc); sl = __reduce_add_sync(HRL_FULL_MASK, sl);
+    if (st.stats) {  // warp-uniform: inactive tail lanes contribute zeros (never guard a *_sync by `active`)
+      const int na = __popc(__ballot_sync(HRL_FULL_MASK, active && k == 0));
+      sc = __reduce_add_sync(HRL_FULL_MASK, active ? sc : 0); sl = __reduce_add_sync(HRL_FULL_MASK, active ? sl : 0);
       if (lane == 0) {
         atomicAdd(&st.stats[0], (unsigned long long)sc); atomicAdd(&st.stats[1], (unsigned long long)sl);
-        atomicAdd(&st.stats[2], (unsigned long long)(ns * 8));
+        atomicAdd(&st.stats[2], (unsigned long long)(ns * na));
       }
     }
   }
@@ -626,6 +627,7 @@ point_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const floa
     break;
   }
   st.base[e * 4 + 0] = make_float4(pos.x, pos.y, pos.z, initial_z);
+  st.base[e * 4 + 1] = make_float4(0.f, 0.f, 0.f, 1.f);  // the cube never rotates
   st.base[e * 4 + 2] = make_float4(vel.x, vel.y, vel.z, 0.f);
   st.misci[e * 2 + 0] = i0;
 #pragma unroll
@@ -870,9 +872,8 @@ int hrl_create(const hrl_config* cfg, int32_t device, hrl_handle** out) {
   CK(cudaFuncSetAttribute(ant_env_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(ant_env_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   *out = h;
-  // identity quaternions so that an un-reset handle is still a valid state
-  rc = hrl_reset(h, nullptr, nullptr, nullptr);
-  if (rc) { hrl_destroy(h); *out = nullptr; return rc; }
+  // like the reference, reset() must be called before the first step(); an un-reset env has a
+  // zero quaternion, produces a non-finite observation and is ended by the NaN guard
   CK(cudaDeviceSynchronize());
   return HRL_OK;
 }
