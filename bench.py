@@ -157,6 +157,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from hrl_pybullet_envs_b200 import VecEnv, _cabi, roofline
+    from hrl_pybullet_envs_b200.sharding import max_over_ranks, shard_offset, sum_episode_stats
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -167,7 +168,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     N = ENVS_PER_GPU
     # shard rule: GPU r owns global envs [r*N, (r+1)*N); no collective on the step path
-    env = VecEnv(ENV_ID, N, device=local, seed=0, env_index_offset=rank * N)
+    env = VecEnv(ENV_ID, N, device=local, seed=0, env_index_offset=shard_offset(rank, N))
     env.reset()
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     ring = torch.rand(64, N, 8, generator=g, device=dev) * 2 - 1          # synthetic U(-1,1) actions, pre-generated
@@ -221,14 +222,10 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop() if sampler else None
 
-    t = torch.tensor([dev_ms, b2b_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # optional episode statistics over NVLink (the only collective in the system; not on the step path)
-        f, i = env.get_state()
-        s = torch.stack([i[:, 1].sum().double(), i[:, 2].sum().double()])
-        dist.all_reduce(s)
-    dev_ms, b2b_ms, e2e_ms = [float(x) for x in t.cpu()]
+    dev_ms, b2b_ms, e2e_ms = max_over_ranks([dev_ms, b2b_ms, e2e_s * 1e3], device=dev)
+    # optional episode statistics over NVLink (the only other collective; not on the step path)
+    f, i = env.get_state()
+    episodes, env_steps = sum_episode_stats(i[:, 1].sum().item(), i[:, 2].sum().item(), device=dev)
 
     if rank == 0:
         hbm_peak, sm_max, which = peaks()
@@ -252,6 +249,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": N * 8 * 4, "d2h_bytes_per_step": N * (46 * 4 + 4 + 1 + 16),
                     "api": "VecEnv.step(numpy) -> hrl_step_host: pinned H2D, kernel, D2H obs/rew/done/info, stream sync"},
             "gpu_launches": int(launches),
+            "episode_stats": {"episodes_started": episodes, "env_steps_total": env_steps},
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": roofline.BYTES_PER_ENV_STEP * N / launch_s / 1e9, "peak": hbm_peak,
                          "unit": "GB/s", "frac": roofline.BYTES_PER_ENV_STEP * N / launch_s / 1e9 / hbm_peak, "traffic": None,
