@@ -11,7 +11,8 @@ import subprocess
 from .config import HrlConfig
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhrl_b200.so")
+# HRL_B200_LIB selects another build of the SAME sources (tuning sweeps: tools/sweep_variants.py)
+LIB_PATH = os.environ.get("HRL_B200_LIB") or os.path.join(_HERE, "libhrl_b200.so")
 SRC_DIR = os.path.join(_HERE, "csrc")
 INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
 _lib = None
@@ -29,21 +30,24 @@ class HrlError(RuntimeError):
     pass
 
 
-def build(force=False, verbose=False):
-    """nvcc -> hrl_pybullet_envs_b200/libhrl_b200.so (cross-compiles without a GPU)."""
+def build(force=False, verbose=False, defines=None, out=None):
+    """nvcc -> hrl_pybullet_envs_b200/libhrl_b200.so (cross-compiles without a GPU).
+    `defines` (e.g. {"HRL_ENVS_PER_WARP": 4}) and `out` build a tuning variant beside it."""
+    out = out or LIB_PATH
     srcs = [os.path.join(SRC_DIR, f) for f in os.listdir(SRC_DIR)] + [os.path.join(INCLUDE_DIR, "hrl_b200.h")]
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
-        return LIB_PATH
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
+        return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(SRC_DIR, "hrl_b200.cu")]
+    dflags = ["-D%s=%s" % kv for kv in sorted((defines or {}).items())]
+    cmd = [nvcc] + NVCC_FLAGS + dflags + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, os.path.join(SRC_DIR, "hrl_b200.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise HrlError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB_PATH
+    return out
 
 
 def lib():

@@ -18,12 +18,30 @@
 #ifndef HRL_MAXC
 #define HRL_MAXC 4  // contacts kept per lane (= per contact group, oracle MAX_CONTACT_PER_GROUP)
 #endif
-#define HRL_NSLOT (2 + 3 * HRL_MAXC)
-// row fields in shared memory: [slot][field][lane]
-enum { RF_JB = 0, RF_JL = 6, RF_WB = 8, RF_Y = 14, RF_DINV = 16, RF_RHS = 17, RF_LAM = 18, RF_N = 19 };
+// envs per warp (4 lanes each).  8 fills the warp.  With fewer, the spare lane groups shadow an env
+// of the same warp (same inputs, same shared-memory slots, identical values; global stores suppressed).
+#ifndef HRL_ENVS_PER_WARP
+#define HRL_ENVS_PER_WARP 8
+#endif
+#define HRL_EPW HRL_ENVS_PER_WARP
+// Constraint rows of one env live in shared memory in VISIT order (Bullet's row order), whitened:
+//   row = a[14] | dinv | rhs  (4 x float4), a = [L^-1 Jb~ (6) ; Ll_k^-1 Jl scattered to leg k (8)]
+// so that "J M^-1 J^T" of two rows is a plain dot product and the same vector is both the row
+// Jacobian and the row response in the transformed velocity dv' = [L^T dvb ; Ll^T g].
+//   rows [0,8)   joint-limit rows (<= 2 per leg), ordered by leg
+//   rows [8,24)  contact normals, ordered by leg then candidate
+//   rows [24,56) friction pairs (2 per contact), same order
+#define HRL_ROW_NRM0 8
+#define HRL_ROW_FRI0 (8 + 4 * HRL_MAXC)
+#define HRL_ROWS_ENV (8 + 12 * HRL_MAXC)
+#define HRL_ROW_IDLE (HRL_ROWS_ENV + 1)        // rows ROWS_ENV, ROWS_ENV+1: all-zero rows / zero impulses for idle visits
+#define HRL_ENV_F4 ((HRL_ROWS_ENV + 2) * 4 + 1)  // float4 per env, +1: the env stride maps the 8 envs of a warp to distinct banks
+#define HRL_LAM_STRIDE (HRL_ROWS_ENV + 3)      // odd: the 8 envs of a warp hit distinct banks
+#define HRL_ROWS_FLOATS_PER_WARP (HRL_EPW * HRL_ENV_F4 * 4)
+#define HRL_LAM_FLOATS_PER_WARP ((HRL_EPW * HRL_LAM_STRIDE + 3) / 4 * 4)
 // contact candidates: [c][field][lane]: P-O (3), n (3), dist, body
 #define HRL_CAND_F 8
-#define HRL_SMEM_FLOATS_PER_WARP ((HRL_NSLOT * RF_N + HRL_MAXC * HRL_CAND_F) * 32)
+#define HRL_SMEM_FLOATS_PER_WARP (HRL_ROWS_FLOATS_PER_WARP + HRL_LAM_FLOATS_PER_WARP + HRL_MAXC * HRL_CAND_F * 32)
 
 struct AntLane {
   // replicated in the 4 lanes of an env
@@ -88,6 +106,7 @@ __host__ __device__ constexpr int sym6(int i, int j) { return i * 6 - (i * (i - 
 
 struct LegDyn {
   float mi11, mi12, mi22;  // Mll^-1
+  float il11, l21, il22;   // Mll = Ll Ll^T: 1/l11, l21, 1/l22
   float G1[6], G2[6];      // base<-joint coupling columns [torque about O; force]
   float K0[6], K1[6];      // (Mll^-1 G^T) rows = G Mll^-1 columns
   float Li[21];            // L^-1 (lower, packed row-major: Li[i*(i+1)/2 + j], j <= i) of S = L L^T
@@ -146,43 +165,126 @@ __device__ __forceinline__ SubstepParams make_params(const hrl_config& cfg) {
   return p;
 }
 
-#define ROW(slot, f) rows[((slot) * RF_N + (f)) * 32 + lane]
-#define ROW_OF(slot, f, l) rows[((slot) * RF_N + (f)) * 32 + (l)]
 #define CAND(c, f) cands[((c) * HRL_CAND_F + (f)) * 32 + lane]
 
-// Finish one constraint row owned by this lane: reduced base Jacobian, response, diagonal, rhs.
-__device__ __forceinline__ void finish_row(float* __restrict__ rows, int lane, int slot, const LegDyn& D,
-                                           const float JB[6], float j1, float j2, const float ub[6], float u1,
-                                           float u2, float pen, float erp, float inv_h, bool positional) {
-  float y1 = D.mi11 * j1 + D.mi12 * j2, y2 = D.mi12 * j1 + D.mi22 * j2;
-  float Jt[6], W[6];
+// Whiten one constraint row of leg k and store it at visit position `pos` of this env's row buffer.
+//   Jb~ = JB - K [j1 j2]^T (leg eliminated), z = L^-1 Jb~, y = Ll^-1 [j1 j2]^T, diag = |z|^2 + |y|^2.
+__device__ __forceinline__ void emit_row(float4* __restrict__ rb, float* __restrict__ lamp, int pos, int k,
+                                         const LegDyn& D, const float JB[6], float j1, float j2, const float ub[6],
+                                         float u1, float u2, float pen, float erp, float inv_h, bool positional) {
+  float Jt[6], z[6];
 #pragma unroll
-  for (int i = 0; i < 6; i++) Jt[i] = JB[i] - (D.G1[i] * y1 + D.G2[i] * y2);
-  sinv_mul(D.Li, Jt, W);
-  float diag = j1 * y1 + j2 * y2, rel = j1 * u1 + j2 * u2;
+  for (int i = 0; i < 6; i++) Jt[i] = JB[i] - (D.K0[i] * j1 + D.K1[i] * j2);
 #pragma unroll
-  for (int i = 0; i < 6; i++) { diag = fmaf(Jt[i], W[i], diag); rel = fmaf(JB[i], ub[i], rel); }
-  float dinv = 1.0f / diag;
+  for (int i = 0; i < 6; i++) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j <= i; j++) a = fmaf(D.Li[i * (i + 1) / 2 + j], Jt[j], a);
+    z[i] = a;
+  }
+  const float y0 = j1 * D.il11, y1 = (j2 - D.l21 * y0) * D.il22;
+  float diag = y0 * y0 + y1 * y1, rel = j1 * u1 + j2 * u2;
+#pragma unroll
+  for (int i = 0; i < 6; i++) { diag = fmaf(z[i], z[i], diag); rel = fmaf(JB[i], ub[i], rel); }
+  const float dinv = 1.0f / diag;
   float posErr = 0.f, velErr = -rel;
   if (positional) {
     if (pen > 0.f) velErr -= pen * inv_h;
     else posErr = -pen * erp * inv_h;
   }
-#pragma unroll
-  for (int i = 0; i < 6; i++) { ROW(slot, RF_JB + i) = Jt[i]; ROW(slot, RF_WB + i) = W[i]; }
-  ROW(slot, RF_JL) = j1; ROW(slot, RF_JL + 1) = j2;
-  ROW(slot, RF_Y) = y1; ROW(slot, RF_Y + 1) = y2;
-  ROW(slot, RF_DINV) = dinv;
-  ROW(slot, RF_RHS) = (posErr + velErr) * dinv;
-  ROW(slot, RF_LAM) = 0.f;
+  float4* r = rb + pos * 4;
+  r[0] = make_float4(z[0], z[1], z[2], z[3]);
+  r[1] = make_float4(z[4], z[5], k == 0 ? y0 : 0.f, k == 0 ? y1 : 0.f);
+  r[2] = make_float4(k == 1 ? y0 : 0.f, k == 1 ? y1 : 0.f, k == 2 ? y0 : 0.f, k == 2 ? y1 : 0.f);
+  r[3] = make_float4(k == 3 ? y0 : 0.f, k == 3 ? y1 : 0.f, dinv, (posErr + velErr) * dinv);
+  lamp[pos] = 0.f;
 }
 
-// One internal step of h = dt/substeps.  `rows`/`cands` point at this WARP's shared memory.
+// ---- Blackwell packed fp32 (FFMA2 / FMUL2 / FADD2): two IEEE-rn fp32 operations per instruction ----
+#define HRL_U64(v) reinterpret_cast<unsigned long long&>(v)
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(HRL_U64(r)) : "l"(HRL_U64(a)), "l"(HRL_U64(b)), "l"(HRL_U64(c)));
+  return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(HRL_U64(r)) : "l"(HRL_U64(a)), "l"(HRL_U64(b)));
+  return r;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(HRL_U64(r)) : "l"(HRL_U64(a)), "l"(HRL_U64(b)));
+  return r;
+}
+
+__device__ __forceinline__ float rsqrt_ftz(float x) {  // MUFU.RSQ without the denormal rescue sequence
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+struct Row { float2 p[7]; float dinv, rhs; };  // a[0..13] as 7 pairs, 1/diag, rhs/diag
+__device__ __forceinline__ Row ld_row(const float4* __restrict__ rb, int r) {
+  const float4 q0 = rb[r * 4], q1 = rb[r * 4 + 1], q2 = rb[r * 4 + 2], q3 = rb[r * 4 + 3];
+  Row R;
+  R.p[0] = make_float2(q0.x, q0.y); R.p[1] = make_float2(q0.z, q0.w); R.p[2] = make_float2(q1.x, q1.y);
+  R.p[3] = make_float2(q1.z, q1.w); R.p[4] = make_float2(q2.x, q2.y); R.p[5] = make_float2(q2.z, q2.w);
+  R.p[6] = make_float2(q3.x, q3.y); R.dinv = q3.z; R.rhs = q3.w;
+  return R;
+}
+__device__ __forceinline__ float dot14(const float2 a[7], const float2 b[7]) {
+  float2 s0 = mul2(a[0], b[0]), s1 = mul2(a[1], b[1]);
+  s0 = fma2(a[2], b[2], s0); s1 = fma2(a[3], b[3], s1);
+  s0 = fma2(a[4], b[4], s0); s1 = fma2(a[5], b[5], s1);
+  s0 = fma2(a[6], b[6], s0);
+  const float2 t = add2(s0, s1);
+  return t.x + t.y;
+}
+__device__ __forceinline__ void axpy14(float2 y[7], const float2 a[7], float s) {
+  const float2 ss = make_float2(s, s);
+#pragma unroll
+  for (int i = 0; i < 7; i++) y[i] = fma2(a[i], ss, y[i]);
+}
+
+// One visit of a single (non-friction) row: clamp the impulse to [0, hi], apply the delta.
+// Idle visits use the all-zero row HRL_ROW_IDLE (a = 0, dinv = rhs = 0, impulse 0): dl = 0 falls out
+// of the arithmetic, no predicate needed.
+template <bool HAS_HI>
+__device__ __forceinline__ void single_visit(float* __restrict__ lamp, float2 dv[7], const Row& R, float lam, int rl,
+                                             float hi) {
+  float dl = fmaf(-dot14(R.p, dv), R.dinv, R.rhs);
+  const float sum = lam + dl;
+  if (HAS_HI) {
+    const float nl = fminf(fmaxf(sum, 0.f), hi);
+    dl = (nl == sum) ? dl : nl - lam;
+  } else {
+    dl = (sum < 0.f) ? -lam : dl;
+  }
+  lamp[rl] = lam + dl;
+  axpy14(dv, R.p, dl);
+}
+// One friction pair with the implicit cone |f| <= mu * lambda_n; skipped (impulses kept) when the
+// normal impulse is zero, like Bullet.
+__device__ __forceinline__ void pair_visit(float* __restrict__ lamp, float2 dv[7], const Row& A, const Row& B, float ln,
+                                           float la, float lb, int ra, float mu) {
+  float na = la + fmaf(-dot14(A.p, dv), A.dinv, A.rhs);
+  float nb = lb + fmaf(-dot14(B.p, dv), B.dinv, B.rhs);
+  const float lim = mu * ln, len2 = fmaf(na, na, nb * nb);
+  const float sc = (len2 > lim * lim) ? lim * rsqrt_ftz(fmaxf(len2, 1e-30f)) : 1.f;
+  const bool on = ln > 0.f;
+  na = on ? na * sc : la; nb = on ? nb * sc : lb;
+  lamp[ra] = na; lamp[ra + 1] = nb;
+  axpy14(dv, A.p, na - la); axpy14(dv, B.p, nb - lb);
+}
+
+// One internal step of h = dt/substeps.  `rows`/`cands` point at this WARP's shared memory
+// (rows: HRL_ROWS_FLOATS_PER_WARP row floats followed by HRL_LAM_FLOATS_PER_WARP impulses).
 // feet_ground: bit set when this leg's foot link (tip or ankle sphere) has a floor manifold at
 // the START of the sub-step (collision detection precedes the dynamics, like Bullet).
 __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, const LegConst& lc, float tau1,
                                             float tau2, float* __restrict__ rows, float* __restrict__ cands,
-                                            int lane, int k, int& feet_ground, int& stat_contacts, int& stat_limits) {
+                                            int lane, int k, int es, int& feet_ground, int& stat_contacts, int& stat_limits) {
   const LegKin K = leg_fk(s, lc);
   const V3 a1 = K.ez, a2 = K.a2;
   const V3 r_ac = K.rh + K.r1;           // aux COM - O
@@ -298,6 +400,7 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
     const float M11 = ant::M_SHORT * dot(lam1a, lam1a) + ant::IZ_SHORT + ant::M_LONG * dot(lam1f, lam1f) + dot(a1, If_a1);
     const float idet = 1.0f / (M11 * M22 - M12 * M12);
     D.mi11 = M22 * idet; D.mi22 = M11 * idet; D.mi12 = -M12 * idet;
+    D.il11 = rsqrtf(M11); D.l21 = M12 * D.il11; D.il22 = rsqrtf(M22 - D.l21 * D.l21);
     const V3 G2f = ant::M_LONG * lam2, G2t = cross(r_fc, G2f) + If_a2;
     const V3 G1fa = ant::M_SHORT * lam1a, G1ff = ant::M_LONG * lam1f;
     const V3 G1f = G1fa + G1ff, G1t = cross(r_ac, G1fa) + ant::IZ_SHORT * a1 + cross(r_fc, G1ff) + If_a1;
@@ -404,17 +507,35 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
     u2 = clampf(fmaf(P.h, qdd2, s.qd2), P.vmax);
   }
 
-  // ---------------- constraint rows owned by this lane ----------------
+  // ---------------- constraint rows: counts, visit positions, whitened rows ----------------
   const float inv_h = 1.0f / P.h;
-  int nL = 0;
+  float4* __restrict__ rb = reinterpret_cast<float4*>(rows) + es * HRL_ENV_F4;  // es: this env's slot in the warp
+  float* __restrict__ lamp = rows + HRL_ROWS_FLOATS_PER_WARP + es * HRL_LAM_STRIDE;
+  const float pl1 = s.q1 - ant::HIP_LO, ph1 = ant::HIP_HI - s.q1;
+  const float pl2 = s.q2 - lc.lo2, ph2 = lc.hi2 - s.q2;
+  // Bullet creates a joint-limit row iff the joint is at or beyond the limit (lo < hi: at most one per joint)
+  const bool lim1 = (pl1 <= 0.f) || (ph1 <= 0.f), lim2 = (pl2 <= 0.f) || (ph2 <= 0.f);
+  const int nL = (int)lim1 + (int)lim2;
+  int incl = nL | (nC << 8);  // inclusive scan over the 4 legs of the env -> Bullet row order
+  {
+    int t = __shfl_up_sync(HRL_FULL_MASK, incl, 1, 4);
+    if (k >= 1) incl += t;
+    t = __shfl_up_sync(HRL_FULL_MASK, incl, 2, 4);
+    if (k >= 2) incl += t;
+  }
+  const int tot = __shfl_sync(HRL_FULL_MASK, incl, 3, 4);
+  const int offL = (incl & 0xff) - nL, offC = (incl >> 8) - nC, NL = tot & 0xff, NC = tot >> 8;
   {
     const float zero6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const float pl1 = s.q1 - ant::HIP_LO, ph1 = ant::HIP_HI - s.q1;
-    const float pl2 = s.q2 - lc.lo2, ph2 = lc.hi2 - s.q2;
-    if (pl1 <= 0.f) { finish_row(rows, lane, nL, D, zero6, 1.f, 0.f, ub, u1, u2, pl1, P.erp_l, inv_h, true); nL++; }
-    if (ph1 <= 0.f) { finish_row(rows, lane, nL, D, zero6, -1.f, 0.f, ub, u1, u2, ph1, P.erp_l, inv_h, true); nL++; }
-    if (pl2 <= 0.f) { finish_row(rows, lane, nL, D, zero6, 0.f, 1.f, ub, u1, u2, pl2, P.erp_l, inv_h, true); nL++; }
-    if (ph2 <= 0.f) { finish_row(rows, lane, nL, D, zero6, 0.f, -1.f, ub, u1, u2, ph2, P.erp_l, inv_h, true); nL++; }
+#pragma unroll 1
+    for (int jj = 0; jj < 2; jj++) {
+      if (!(jj ? lim2 : lim1)) continue;
+      const float pl = jj ? pl2 : pl1, ph = jj ? ph2 : ph1;
+      const bool lo = pl <= 0.f;
+      const float sg = lo ? 1.f : -1.f, pen = lo ? pl : ph;
+      emit_row(rb, lamp, offL + (jj ? (int)lim1 : 0), k, D, zero6, jj ? 0.f : sg, jj ? sg : 0.f, ub, u1, u2, pen,
+               P.erp_l, inv_h, true);
+    }
   }
   for (int c = 0; c < nC; c++) {
     const V3 Pr = mk(CAND(c, 0), CAND(c, 1), CAND(c, 2));
@@ -423,105 +544,93 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
     V3 t1, t2;
     plane_space(n, t1, t2);
     const V3 Ph = Pr - K.rh, Pa = Pr - r_ank;
-#pragma unroll
+    const int ci = offC + c;
+#pragma unroll 1
     for (int di = 0; di < 3; di++) {
       const V3 d = di == 0 ? n : (di == 1 ? t1 : t2);
       const V3 jt = cross(Pr, d);
       const float JB[6] = {jt.x, jt.y, jt.z, d.x, d.y, d.z};
       const float j1 = body >= 1.f ? dot(a1, cross(Ph, d)) : 0.f;
       const float j2 = body >= 2.f ? dot(a2, cross(Pa, d)) : 0.f;
-      finish_row(rows, lane, 2 + 3 * c + di, D, JB, j1, j2, ub, u1, u2, dist, P.erp_c, inv_h, di == 0);
+      const int pos = di == 0 ? HRL_ROW_NRM0 + ci : HRL_ROW_FRI0 + 2 * ci + (di - 1);
+      emit_row(rb, lamp, pos, k, D, JB, j1, j2, ub, u1, u2, dist, P.erp_c, inv_h, di == 0);
     }
   }
   stat_contacts += nC; stat_limits += nL;
   __syncwarp();
 
   // ---------------- projected Gauss-Seidel, Bullet row order ----------------
-  float dvb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, g1 = 0.f, g2 = 0.f;
-  const int gbase = lane & ~3;
+  // Every lane of the env evaluates every row (broadcast shared-memory reads, no shuffle on the
+  // dependency chain).  A single warp issues at most one instruction per ~2 cycles, so the sweep is
+  // bound by its instruction count: packed FFMA2 arithmetic, rows prefetched one visit ahead into
+  // ping-pong registers, trip counts = maxima over the envs of the warp, idle visits on a zero row.
+  float2 dv[7];
+#pragma unroll
+  for (int i = 0; i < 7; i++) dv[i] = make_float2(0.f, 0.f);
+  const int maxNL = __reduce_max_sync(HRL_FULL_MASK, NL), maxNC = __reduce_max_sync(HRL_FULL_MASK, NC);
+#define HRL_LIM_ROW(t) (((t) < NL) ? lbase + lstep * (t) : HRL_ROW_IDLE)
+#define HRL_NRM_ROW(t) (((t) < NC) ? HRL_ROW_NRM0 + (t) : HRL_ROW_IDLE)
+#define HRL_FRI_ROW(t) (((t) < NC) ? HRL_ROW_FRI0 + 2 * (t) : HRL_ROW_IDLE - 1)
   for (int it = 0; it < P.iters; it++) {
     // (1) joint-limit rows; Bullet walks the non-contact rows backwards on even iterations
-    for (int idx = 0; idx < 8; idx++) {
-      const int o = (it & 1) ? (idx >> 1) : 3 - (idx >> 1);
-      const int j = (it & 1) ? (idx & 1) : 1 - (idx & 1);
-      const bool mine = (k == o) && (j < nL);
-      if (!__any_sync(HRL_FULL_MASK, mine)) continue;
-      float dl = 0.f;
-      if (mine) {
-        float jd = ROW(j, RF_JL) * g1 + ROW(j, RF_JL + 1) * g2;
-#pragma unroll
-        for (int i = 0; i < 6; i++) jd = fmaf(ROW(j, RF_JB + i), dvb[i], jd);
-        const float lam = ROW(j, RF_LAM);
-        dl = ROW(j, RF_RHS) - jd * ROW(j, RF_DINV);
-        const float sum = lam + dl;
-        if (sum < 0.f) dl = -lam; else if (sum > P.max_imp) dl = P.max_imp - lam;
-        ROW(j, RF_LAM) = lam + dl;
-        g1 = fmaf(ROW(j, RF_Y), dl, g1); g2 = fmaf(ROW(j, RF_Y + 1), dl, g2);
-      }
-      dl = __shfl_sync(HRL_FULL_MASK, dl, gbase | o);
-      if (dl != 0.f) {
-#pragma unroll
-        for (int i = 0; i < 6; i++) dvb[i] = fmaf(ROW_OF(j, RF_WB + i, gbase | o), dl, dvb[i]);
+    if (maxNL > 0) {
+      const int lbase = (it & 1) ? 0 : NL - 1, lstep = (it & 1) ? 1 : -1;
+      int r0 = HRL_LIM_ROW(0), r1;
+      Row R0 = ld_row(rb, r0), R1;
+      float l0 = lamp[r0], l1;
+      for (int t = 0; t < maxNL; t += 2) {
+        r1 = HRL_LIM_ROW(t + 1); R1 = ld_row(rb, r1); l1 = lamp[r1];
+        single_visit<true>(lamp, dv, R0, l0, r0, P.max_imp);
+        r0 = HRL_LIM_ROW(t + 2); R0 = ld_row(rb, r0); l0 = lamp[r0];
+        single_visit<true>(lamp, dv, R1, l1, r1, P.max_imp);
       }
     }
-    // (2) contact normals
-    for (int o = 0; o < 4; o++)
-      for (int c = 0; c < HRL_MAXC; c++) {
-        const bool mine = (k == o) && (c < nC);
-        if (!__any_sync(HRL_FULL_MASK, mine)) continue;
-        const int sl = 2 + 3 * c;
-        float dl = 0.f;
-        if (mine) {
-          float jd = ROW(sl, RF_JL) * g1 + ROW(sl, RF_JL + 1) * g2;
-#pragma unroll
-          for (int i = 0; i < 6; i++) jd = fmaf(ROW(sl, RF_JB + i), dvb[i], jd);
-          const float lam = ROW(sl, RF_LAM);
-          dl = ROW(sl, RF_RHS) - jd * ROW(sl, RF_DINV);
-          if (lam + dl < 0.f) dl = -lam;
-          ROW(sl, RF_LAM) = lam + dl;
-          g1 = fmaf(ROW(sl, RF_Y), dl, g1); g2 = fmaf(ROW(sl, RF_Y + 1), dl, g2);
-        }
-        dl = __shfl_sync(HRL_FULL_MASK, dl, gbase | o);
-        if (dl != 0.f) {
-#pragma unroll
-          for (int i = 0; i < 6; i++) dvb[i] = fmaf(ROW_OF(sl, RF_WB + i, gbase | o), dl, dvb[i]);
+    if (maxNC > 0) {
+      // (2) contact normals
+      {
+        int r0 = HRL_NRM_ROW(0), r1;
+        Row R0 = ld_row(rb, r0), R1;
+        float l0 = lamp[r0], l1;
+        for (int t = 0; t < maxNC; t += 2) {
+          r1 = HRL_NRM_ROW(t + 1); R1 = ld_row(rb, r1); l1 = lamp[r1];
+          single_visit<false>(lamp, dv, R0, l0, r0, 0.f);
+          r0 = HRL_NRM_ROW(t + 2); R0 = ld_row(rb, r0); l0 = lamp[r0];
+          single_visit<false>(lamp, dv, R1, l1, r1, 0.f);
         }
       }
-    // (3) friction pairs with the implicit cone |f| <= mu * lambda_n
-    for (int o = 0; o < 4; o++)
-      for (int c = 0; c < HRL_MAXC; c++) {
-        const int sl = 2 + 3 * c;
-        const bool mine = (k == o) && (c < nC) && (ROW(sl, RF_LAM) > 0.f);
-        if (!__any_sync(HRL_FULL_MASK, mine)) continue;
-        float da = 0.f, db = 0.f;
-        if (mine) {
-          const int sa = sl + 1, sb = sl + 2;
-          float ja = ROW(sa, RF_JL) * g1 + ROW(sa, RF_JL + 1) * g2;
-          float jb = ROW(sb, RF_JL) * g1 + ROW(sb, RF_JL + 1) * g2;
-#pragma unroll
-          for (int i = 0; i < 6; i++) { ja = fmaf(ROW(sa, RF_JB + i), dvb[i], ja); jb = fmaf(ROW(sb, RF_JB + i), dvb[i], jb); }
-          const float la = ROW(sa, RF_LAM), lb = ROW(sb, RF_LAM);
-          float na = la + (ROW(sa, RF_RHS) - ja * ROW(sa, RF_DINV));
-          float nb = lb + (ROW(sb, RF_RHS) - jb * ROW(sb, RF_DINV));
-          const float lim = P.mu * ROW(sl, RF_LAM), len2 = na * na + nb * nb;
-          if (len2 > lim * lim) { const float sc = lim * rsqrtf(len2); na *= sc; nb *= sc; }
-          da = na - la; db = nb - lb;
-          ROW(sa, RF_LAM) = na; ROW(sb, RF_LAM) = nb;
-          g1 = fmaf(ROW(sa, RF_Y), da, fmaf(ROW(sb, RF_Y), db, g1));
-          g2 = fmaf(ROW(sa, RF_Y + 1), da, fmaf(ROW(sb, RF_Y + 1), db, g2));
-        }
-        da = __shfl_sync(HRL_FULL_MASK, da, gbase | o);
-        db = __shfl_sync(HRL_FULL_MASK, db, gbase | o);
-        if (da != 0.f || db != 0.f) {
-#pragma unroll
-          for (int i = 0; i < 6; i++)
-            dvb[i] = fmaf(ROW_OF(sl + 1, RF_WB + i, gbase | o), da, fmaf(ROW_OF(sl + 2, RF_WB + i, gbase | o), db, dvb[i]));
+      // (3) friction pairs
+      {
+        int r0 = HRL_FRI_ROW(0), r1;
+        Row A0 = ld_row(rb, r0), B0 = ld_row(rb, r0 + 1), A1, B1;
+        float n0 = lamp[HRL_NRM_ROW(0)], a0 = lamp[r0], b0 = lamp[r0 + 1], n1, a1, b1;
+        for (int t = 0; t < maxNC; t += 2) {
+          r1 = HRL_FRI_ROW(t + 1); A1 = ld_row(rb, r1); B1 = ld_row(rb, r1 + 1);
+          n1 = lamp[HRL_NRM_ROW(t + 1)]; a1 = lamp[r1]; b1 = lamp[r1 + 1];
+          pair_visit(lamp, dv, A0, B0, n0, a0, b0, r0, P.mu);
+          r0 = HRL_FRI_ROW(t + 2); A0 = ld_row(rb, r0); B0 = ld_row(rb, r0 + 1);
+          n0 = lamp[HRL_NRM_ROW(t + 2)]; a0 = lamp[r0]; b0 = lamp[r0 + 1];
+          pair_visit(lamp, dv, A1, B1, n1, a1, b1, r1, P.mu);
         }
       }
+    }
   }
+#undef HRL_LIM_ROW
+#undef HRL_NRM_ROW
+#undef HRL_FRI_ROW
   __syncwarp();
 
-  // ---------------- apply, clamp, integrate ----------------
+  // ---------------- back to physical velocities, clamp, integrate ----------------
+  float dvb[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {  // dvb = L^-T dvb'
+    float a = 0.f;
+#pragma unroll
+    for (int j = i; j < 6; j++) a = fmaf(D.Li[j * (j + 1) / 2 + i], (j & 1) ? dv[j >> 1].y : dv[j >> 1].x, a);
+    dvb[i] = a;
+  }
+  const float2 gp = k == 0 ? dv[3] : (k == 1 ? dv[4] : (k == 2 ? dv[5] : dv[6]));
+  const float gp0 = gp.x, gp1 = gp.y;
+  const float g2 = gp1 * D.il22, g1 = (gp0 - D.l21 * g2) * D.il11;  // g = Ll^-T g'
   float dq1 = g1, dq2 = g2;
 #pragma unroll
   for (int i = 0; i < 6; i++) { dq1 = fmaf(-D.K0[i], dvb[i], dq1); dq2 = fmaf(-D.K1[i], dvb[i], dq2); }

@@ -108,7 +108,7 @@ struct TaskRegs {  // replicated per-env task state held in registers
 //   mode 0: full env step (+ auto-reset), mode 1: n_sub physics sub-steps only,
 //   mode 2: reset the masked envs and emit their observation, mode 3: observe only.
 // ------------------------------------------------------------------------------------------
-#define SMEM_PER_WARP_FLOATS (HRL_SMEM_FLOATS_PER_WARP + 8 * HRL_OBS_STAGE + 2 * 8 * 2 * HRL_MAX_BINS)
+#define SMEM_PER_WARP_FLOATS (HRL_SMEM_FLOATS_PER_WARP + HRL_EPW * HRL_OBS_STAGE + 2 * HRL_EPW * 2 * HRL_MAX_BINS)
 
 template <int FAMILY>
 __global__ void __launch_bounds__(32 * HRL_WARPS_PER_CTA)
@@ -116,17 +116,18 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
                const float* __restrict__ actions, const uint8_t* __restrict__ mask, float* __restrict__ obs_out,
                float* __restrict__ rew_out, uint8_t* __restrict__ done_out, float* __restrict__ info_out,
                float* __restrict__ term_out, int mode, int n_sub, int D) {
-  extern __shared__ float smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, k = lane & 3, ew = lane >> 2;
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, k = lane & 3, ew = lane >> 2, es = ew % HRL_EPW;
   float* rows = smem + warp * SMEM_PER_WARP_FLOATS;
-  float* cands = rows + HRL_NSLOT * RF_N * 32;
-  float* sobs = cands + HRL_MAXC * HRL_CAND_F * 32;                               // [8][HRL_OBS_STAGE]
-  unsigned long long* sbins = (unsigned long long*)(sobs + 8 * HRL_OBS_STAGE);   // [8][2][HRL_MAX_BINS]
+  float* cands = rows + HRL_ROWS_FLOATS_PER_WARP + HRL_LAM_FLOATS_PER_WARP;
+  float* sobs = cands + HRL_MAXC * HRL_CAND_F * 32;                               // [EPW][HRL_OBS_STAGE]
+  unsigned long long* sbins = (unsigned long long*)(sobs + HRL_EPW * HRL_OBS_STAGE);   // [EPW][2][HRL_MAX_BINS]
   const int N = cfg.num_envs, kind = cfg.env_kind;
-  const int env_raw = (blockIdx.x * (32 * HRL_WARPS_PER_CTA) + threadIdx.x) >> 2;
-  const bool active = env_raw < N;
-  const int e = active ? env_raw : N - 1;
-  const int env0 = (blockIdx.x * (32 * HRL_WARPS_PER_CTA) + warp * 32) >> 2;  // first env of this warp
+  const int env0 = (blockIdx.x * HRL_WARPS_PER_CTA + warp) * HRL_EPW;  // first env of this warp
+  const int env_raw = env0 + ew;
+  const bool active = (ew < HRL_EPW) && (env_raw < N);
+  // idle lane groups shadow an env of their own warp (same trip counts, stores suppressed)
+  const int e = active ? env_raw : min(env0 + (ew % HRL_EPW), N - 1);
   const uint32_t genv = (uint32_t)(cfg.env_index_offset + e);
   const LegConst lc = leg_const(k);
 
@@ -157,6 +158,10 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
   float act1 = 0.f, act2 = 0.f;
   int feet_ground = 0;
   if (mode <= 1) {
+    // the branch-free solver multiplies idle (stale) rows by 0: they must be finite
+    for (int i = lane; i < (HRL_ROWS_FLOATS_PER_WARP + HRL_LAM_FLOATS_PER_WARP) / 4; i += 32)
+      reinterpret_cast<float4*>(rows)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
     const float2 a = reinterpret_cast<const float2*>(actions)[e * 4 + k];
     act1 = a.x; act2 = a.y;
     // WalkerBase.apply_action [3P-MEM]: clip to +-1, torque = power * power_coef * a
@@ -167,7 +172,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
     const int ns = mode == 0 ? cfg.substeps : n_sub;
     for (int i = 0; i < ns; i++) {
       const bool on = (i == 0) || !cfg.torque_first_substep_only;
-      ant_substep(s, P, lc, on ? tau1 : 0.f, on ? tau2 : 0.f, rows, cands, lane, k, feet_ground, sc, sl);
+      ant_substep(s, P, lc, on ? tau1 : 0.f, on ? tau2 : 0.f, rows, cands, lane, k, es, feet_ground, sc, sl);
     }
     if (st.stats) {  // warp-uniform: inactive tail lanes contribute zeros (never guard a *_sync by `active`)
       const int na = __popc(__ballot_sync(HRL_FULL_MASK, active && k == 0));
@@ -259,7 +264,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       wtd_new = sqrtf(dx * dx + dy * dy);
       sincosf(atan2f(dy, dx) - yaw, &sin_t, &cos_t);
     }
-    float* so = sobs + ew * HRL_OBS_STAGE;
+    float* so = sobs + es * D;  // dense staging: the warp's observations are one contiguous span
     const bool commit = (todo == 1);
     int fin = 1;       // finite flag (this lane's values)
     int switched = 0;  // Flagrun: the target changed in this step
@@ -285,7 +290,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       food_rew = gsum(food_rew);
       // sector sensor (:128-177): nearest item wins per bin
       const int nb = cfg.n_bins;
-      for (int i = lane; i < 8 * 2 * HRL_MAX_BINS; i += 32) sbins[i] = 0x7ff0000000000000ull;
+      for (int i = lane; i < HRL_EPW * 2 * HRL_MAX_BINS; i += 32) sbins[i] = 0x7ff0000000000000ull;
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 4; i++) {
@@ -293,7 +298,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
         if (gi >= cfg.n_food + cfg.n_poison) continue;
         double d2;
         const int b = gather_item_bin(s.O.x, s.O.y, yaw, it_x[i], it_y[i], nb, cfg.sensor_range, cfg.sensor_span, &d2);
-        if (b >= 0) atomicMin(&sbins[(ew * 2 + (gi < cfg.n_food ? 0 : 1)) * HRL_MAX_BINS + b], (unsigned long long)__double_as_longlong(d2));
+        if (b >= 0) atomicMin(&sbins[(es * 2 + (gi < cfg.n_food ? 0 : 1)) * HRL_MAX_BINS + b], (unsigned long long)__double_as_longlong(d2));
       }
       __syncwarp();
       if (commit) {
@@ -304,7 +309,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
         so[6 + 4 * k] = clip5(rel1); so[7 + 4 * k] = clip5(sp1); so[8 + 4 * k] = clip5(rel2); so[9 + 4 * k] = clip5(sp2);
         for (int b = k; b < 2 * nb; b += 4) {
           const int ty = b / nb, bb = b - ty * nb;
-          const unsigned long long bits = sbins[(ew * 2 + ty) * HRL_MAX_BINS + bb];
+          const unsigned long long bits = sbins[(es * 2 + ty) * HRL_MAX_BINS + bb];
           so[26 + b] = bits == 0x7ff0000000000000ull ? 0.f : (float)(1.0 - __longlong_as_double((long long)bits) / (double)cfg.sensor_range);
         }
       }
@@ -442,9 +447,9 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
     const unsigned need_mask = __ballot_sync(HRL_FULL_MASK, next_todo == 3);
     if (need_mask && term_out) {
       __syncwarp();
-      for (int i = lane; i < 8 * D; i += 32) {
-        const int w8 = i / D, c = i - w8 * D;
-        if (((need_mask >> (4 * w8)) & 1u) && env0 + w8 < N) term_out[(size_t)(env0 + w8) * D + c] = sobs[w8 * HRL_OBS_STAGE + c];
+      for (int i = lane; i < HRL_EPW * D; i += 32) {
+        const int w8 = i / D;
+        if (((need_mask >> (4 * w8)) & 1u) && env0 + w8 < N) term_out[(size_t)env0 * D + i] = sobs[i];
       }
       __syncwarp();
     }
@@ -478,9 +483,15 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       const bool m = mask ? (mask[e] != 0) : true;
       wmask = __ballot_sync(HRL_FULL_MASK, m);
     }
-    for (int i = lane; i < 8 * D; i += 32) {
-      const int w8 = i / D, c = i - w8 * D;
-      if (env0 + w8 < N && ((wmask >> (4 * w8)) & 1u)) obs_out[(size_t)(env0 + w8) * D + c] = sobs[w8 * HRL_OBS_STAGE + c];
+    float* dst = obs_out + (size_t)env0 * D;
+    if (env0 + HRL_EPW <= N && wmask == 0xffffffffu && ((HRL_EPW * D) & 3) == 0 && (((uintptr_t)dst & 15) == 0)) {
+      // common case: one contiguous, 16-byte aligned span -> float4 stores, no index arithmetic
+      for (int i = lane; i < HRL_EPW * D / 4; i += 32) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(sobs)[i];
+    } else {
+      for (int i = lane; i < HRL_EPW * D; i += 32) {
+        const int w8 = i / D;
+        if (env0 + w8 < N && ((wmask >> (4 * w8)) & 1u)) dst[i] = sobs[i];
+      }
     }
   }
 }
@@ -740,7 +751,11 @@ static int scene_bounds(const hrl_config* cfg, float* b) {
 extern "C" {
 
 const char* hrl_last_error(void) { return g_err; }
-const char* hrl_version(void) { return "hrl_b200 0.1 (sm_100a; 4 lanes/env; MAXC=" "4" ")"; }
+#define HRL_STR2(x) #x
+#define HRL_STR(x) HRL_STR2(x)
+const char* hrl_version(void) {
+  return "hrl_b200 0.2 (sm_100a; 4 lanes/env; " HRL_STR(HRL_ENVS_PER_WARP) " envs/warp; " HRL_STR(HRL_WARPS_PER_CTA) " warps/CTA; MAXC=" HRL_STR(HRL_MAXC) ")";
+}
 int64_t hrl_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int hrl_default_config(int32_t kind, int32_t num_envs, hrl_config* c) {
@@ -885,7 +900,7 @@ static int launch_env(hrl_handle* h, int mode, int n_sub, const float* act, cons
     const int B = 128, G = (h->N + B - 1) / B;
     point_env_kernel<<<G, B, 0, s>>>(h->cfg, h->st, act, mask, obs, rew, done, info, term, mode, n_sub, h->D);
   } else {
-    const int T = 32 * HRL_WARPS_PER_CTA, G = (h->N * 4 + T - 1) / T;
+    const int T = 32 * HRL_WARPS_PER_CTA, EPC = HRL_EPW * HRL_WARPS_PER_CTA, G = (h->N + EPC - 1) / EPC;
     const size_t smem = (size_t)HRL_WARPS_PER_CTA * SMEM_PER_WARP_FLOATS * sizeof(float);
     if (h->cfg.env_kind == HRL_ANT_GATHER)
       ant_env_kernel<0><<<G, T, smem, s>>>(h->cfg, h->st, h->d_bounds, h->n_lines, act, mask, obs, rew, done, info, term, mode, n_sub, h->D);
