@@ -22,7 +22,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 # every symbol include/hrl_b200.h declares (checked by tests/test_cabi_symbols.py)
 SYMBOLS = ["hrl_default_config", "hrl_obs_dim", "hrl_act_dim", "hrl_create", "hrl_destroy", "hrl_reset", "hrl_step",
-           "hrl_step_host", "hrl_get_state", "hrl_set_state", "hrl_observe", "hrl_gather_sensor", "hrl_sense_walls",
+           "hrl_step_host", "hrl_set_host_mode", "hrl_host_layout", "hrl_get_state", "hrl_set_state", "hrl_observe", "hrl_gather_sensor", "hrl_sense_walls",
            "hrl_substeps", "hrl_launch_count", "hrl_last_error", "hrl_version"]
 
 
@@ -67,6 +67,8 @@ def lib():
     L.hrl_reset.argtypes = [vp, vp, vp, vp]
     L.hrl_step.argtypes = [vp] + [vp] * 7
     L.hrl_step_host.argtypes = [vp] + [vp] * 6
+    L.hrl_set_host_mode.argtypes = [vp, i32]
+    L.hrl_host_layout.argtypes = [C.POINTER(HrlConfig)] + [C.POINTER(C.c_size_t)] * 4
     L.hrl_get_state.argtypes = [vp, vp, vp, vp]
     L.hrl_set_state.argtypes = [vp, vp, vp, vp]
     L.hrl_observe.argtypes = [vp, vp, vp]

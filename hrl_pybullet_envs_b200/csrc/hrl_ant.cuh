@@ -87,8 +87,8 @@ __device__ __forceinline__ LegKin leg_fk(const AntLane& s, const LegConst& c) {
   V3 d0 = c.sx * K.ex + c.sy * K.ey;
   K.rh = 0.2f * d0;
   float s1, c1, s2, c2;
-  sincosf(s.q1, &s1, &c1);
-  sincosf(s.q2, &s2, &c2);
+  __sincosf(s.q1, &s1, &c1);  // |q| < 2 rad: MUFU sin/cos, abs error ~5e-7
+  __sincosf(s.q2, &s2, &c2);
   V3 auxx = c1 * K.ex + s1 * K.ey, auxy = c1 * K.ey - s1 * K.ex;
   V3 d1 = c.sx * auxx + c.sy * auxy;
   K.r1 = 0.1f * d1;
@@ -136,18 +136,18 @@ __device__ __forceinline__ float clampf(float x, float lim) { return fminf(fmaxf
 // Bullet btPlaneSpace1
 __device__ __forceinline__ void plane_space(V3 n, V3& p, V3& q) {
   if (fabsf(n.z) > 0.7071067811865475244f) {
-    float a = n.y * n.y + n.z * n.z, k = rsqrtf(a);
+    float a = n.y * n.y + n.z * n.z, k = rsqrt_ftz(a);
     p = mk(0.f, -n.z * k, n.y * k);
     q = mk(a * k, -n.x * p.z, n.x * p.y);
   } else {
-    float a = n.x * n.x + n.y * n.y, k = rsqrtf(a);
+    float a = n.x * n.x + n.y * n.y, k = rsqrt_ftz(a);
     p = mk(-n.y * k, n.x * k, 0.f);
     q = mk(-n.z * p.y, n.z * p.x, a * k);
   }
 }
 
 struct SubstepParams {
-  float h, g, kl, ka, erp_c, erp_l, mu, max_imp, vmax, margin, gz;
+  float h, inv_h, g, kl, ka, erp_c, erp_l, mu, max_imp, vmax, margin, gz;
   float wx, wy;  // wall inner faces at +-wx, +-wy
   int has_walls, has_box, iters;
   float blo[3], bhi[3];
@@ -155,7 +155,7 @@ struct SubstepParams {
 
 __device__ __forceinline__ SubstepParams make_params(const hrl_config& cfg) {
   SubstepParams p;
-  p.h = cfg.dt / (float)cfg.substeps; p.g = cfg.gravity; p.kl = cfg.lin_damping; p.ka = cfg.ang_damping;
+  p.h = cfg.dt / (float)cfg.substeps; p.inv_h = 1.0f / p.h; p.g = cfg.gravity; p.kl = cfg.lin_damping; p.ka = cfg.ang_damping;
   p.erp_c = cfg.contact_erp; p.erp_l = cfg.limit_erp; p.mu = cfg.friction; p.max_imp = cfg.limit_max_impulse;
   p.vmax = cfg.max_coord_vel; p.margin = cfg.contact_margin; p.gz = cfg.ground_z;
   p.wx = cfg.world_size[0] * 0.5f - 0.05f; p.wy = cfg.world_size[1] * 0.5f - 0.05f;
@@ -186,7 +186,7 @@ __device__ __forceinline__ void emit_row(float4* __restrict__ rb, float* __restr
   float diag = y0 * y0 + y1 * y1, rel = j1 * u1 + j2 * u2;
 #pragma unroll
   for (int i = 0; i < 6; i++) { diag = fmaf(z[i], z[i], diag); rel = fmaf(JB[i], ub[i], rel); }
-  const float dinv = 1.0f / diag;
+  const float dinv = rcp_ftz(diag);
   float posErr = 0.f, velErr = -rel;
   if (positional) {
     if (pen > 0.f) velErr -= pen * inv_h;
@@ -215,12 +215,6 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
 __device__ __forceinline__ float2 add2(float2 a, float2 b) {
   float2 r;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(HRL_U64(r)) : "l"(HRL_U64(a)), "l"(HRL_U64(b)));
-  return r;
-}
-
-__device__ __forceinline__ float rsqrt_ftz(float x) {  // MUFU.RSQ without the denormal rescue sequence
-  float r;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 
@@ -297,63 +291,65 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
   int nC = 0;
   feet_ground = 0;
   {
-    // candidate order inside the group: [torso sphere (lane 0)], tip (foot), ankle (aux), hip (torso)
+    // candidate order inside the group: [torso sphere (lane 0)], tip (foot), ankle (aux), hip (torso);
+    // per sphere: ground, walls +x -x +y -y, box.  Rolled on purpose (code size); the four wall tests
+    // hide behind one comparison because a wall contact is rare.
+    auto add = [&](V3 crel, float r, V3 n, float dist, float body) {
+      if (nC < HRL_MAXC) {
+        const V3 Prel = crel - r * n;  // contact point on the robot, relative to O
+        CAND(nC, 0) = Prel.x; CAND(nC, 1) = Prel.y; CAND(nC, 2) = Prel.z;
+        CAND(nC, 3) = n.x; CAND(nC, 4) = n.y; CAND(nC, 5) = n.z;
+        CAND(nC, 6) = dist; CAND(nC, 7) = body;
+        nC++;
+      }
+    };
+#pragma unroll 1
+    for (int si = (k == 0 ? 0 : 1); si < 4; si++) {
+      const V3 crel = si == 0 ? mk(0.f, 0.f, 0.f) : (si == 1 ? r_tip : (si == 2 ? r_ank : K.rh));
+      const float r = si == 0 ? ant::R_TORSO : ant::R_CAPS;
+      const float body = si == 1 ? 2.f : (si == 2 ? 1.f : 0.f);
+      const V3 c = s.O + crel;
+      const float dg = c.z - P.gz - r;
+      if (dg < P.margin) {
+        if (si == 1 || si == 2) feet_ground = 1;
+        add(crel, r, mk(0.f, 0.f, 1.f), dg, body);
+      }
+      if (P.has_walls && fminf(P.wx - fabsf(c.x), P.wy - fabsf(c.y)) - r < P.margin) {
+        float d;
+        d = P.wx - c.x - r; if (d < P.margin) add(crel, r, mk(-1.f, 0.f, 0.f), d, body);
+        d = c.x + P.wx - r; if (d < P.margin) add(crel, r, mk(1.f, 0.f, 0.f), d, body);
+        d = P.wy - c.y - r; if (d < P.margin) add(crel, r, mk(0.f, -1.f, 0.f), d, body);
+        d = c.y + P.wy - r; if (d < P.margin) add(crel, r, mk(0.f, 1.f, 0.f), d, body);
+      }
+      if (P.has_box) {
+        // sphere vs AABB
+        const float cc[3] = {c.x, c.y, c.z};
+        float qq[3];
+        bool inside = true;
 #pragma unroll
-    for (int si = 0; si < 4; si++) {
-      if (si == 0 && k != 0) continue;
-      V3 crel = si == 0 ? mk(0.f, 0.f, 0.f) : (si == 1 ? r_tip : (si == 2 ? r_ank : K.rh));
-      float r = si == 0 ? ant::R_TORSO : ant::R_CAPS;
-      float body = si == 0 ? 0.f : (si == 1 ? 2.f : (si == 2 ? 1.f : 0.f));
-      bool isfoot = (si == 1 || si == 2);
-      V3 c = s.O + crel;
-#pragma unroll
-      for (int surf = 0; surf < 6; surf++) {
+        for (int i = 0; i < 3; i++) {
+          float xx = cc[i];
+          if (xx < P.blo[i]) { xx = P.blo[i]; inside = false; }
+          if (xx > P.bhi[i]) { xx = P.bhi[i]; inside = false; }
+          qq[i] = xx;
+        }
         V3 n; float dist;
-        if (surf == 0) { n = mk(0.f, 0.f, 1.f); dist = c.z - P.gz - r; }
-        else if (surf <= 4) {
-          if (!P.has_walls) continue;
-          if (surf == 1) { n = mk(-1.f, 0.f, 0.f); dist = P.wx - c.x - r; }
-          else if (surf == 2) { n = mk(1.f, 0.f, 0.f); dist = c.x + P.wx - r; }
-          else if (surf == 3) { n = mk(0.f, -1.f, 0.f); dist = P.wy - c.y - r; }
-          else { n = mk(0.f, 1.f, 0.f); dist = c.y + P.wy - r; }
+        if (!inside) {
+          const V3 d = mk(cc[0] - qq[0], cc[1] - qq[1], cc[2] - qq[2]);
+          const float len = sqrtf(dot(d, d));
+          n = (1.0f / len) * d; dist = len - r;
         } else {
-          if (!P.has_box) continue;
-          // sphere vs AABB
-          float cc[3] = {c.x, c.y, c.z}, qq[3];
-          bool inside = true;
+          float best = 1e30f; int bi = 0; float bs = 1.f;
 #pragma unroll
           for (int i = 0; i < 3; i++) {
-            float xx = cc[i];
-            if (xx < P.blo[i]) { xx = P.blo[i]; inside = false; }
-            if (xx > P.bhi[i]) { xx = P.bhi[i]; inside = false; }
-            qq[i] = xx;
+            const float dl = cc[i] - P.blo[i], dh = P.bhi[i] - cc[i];
+            if (dl < best) { best = dl; bi = i; bs = -1.f; }
+            if (dh < best) { best = dh; bi = i; bs = 1.f; }
           }
-          if (!inside) {
-            V3 d = mk(cc[0] - qq[0], cc[1] - qq[1], cc[2] - qq[2]);
-            float len = norm(d);
-            n = (1.0f / len) * d; dist = len - r;
-          } else {
-            float best = 1e30f; int bi = 0; float bs = 1.f;
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-              float dl = cc[i] - P.blo[i], dh = P.bhi[i] - cc[i];
-              if (dl < best) { best = dl; bi = i; bs = -1.f; }
-              if (dh < best) { best = dh; bi = i; bs = 1.f; }
-            }
-            n = mk(bi == 0 ? bs : 0.f, bi == 1 ? bs : 0.f, bi == 2 ? bs : 0.f);
-            dist = -best - r;
-          }
+          n = mk(bi == 0 ? bs : 0.f, bi == 1 ? bs : 0.f, bi == 2 ? bs : 0.f);
+          dist = -best - r;
         }
-        if (dist < P.margin) {
-          if (surf == 0 && isfoot) feet_ground = 1;
-          if (nC < HRL_MAXC) {
-            V3 Prel = crel - r * n;  // contact point on the robot, relative to O
-            CAND(nC, 0) = Prel.x; CAND(nC, 1) = Prel.y; CAND(nC, 2) = Prel.z;
-            CAND(nC, 3) = n.x; CAND(nC, 4) = n.y; CAND(nC, 5) = n.z;
-            CAND(nC, 6) = dist; CAND(nC, 7) = body;
-            nC++;
-          }
-        }
+        if (dist < P.margin) add(crel, r, n, dist, body);
       }
     }
   }
@@ -398,9 +394,9 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
     const float M22 = ant::M_LONG * dot(lam2, lam2) + ant::IX_LONG;
     const float M12 = ant::M_LONG * dot(lam1f, lam2) + dot(a1, If_a2);
     const float M11 = ant::M_SHORT * dot(lam1a, lam1a) + ant::IZ_SHORT + ant::M_LONG * dot(lam1f, lam1f) + dot(a1, If_a1);
-    const float idet = 1.0f / (M11 * M22 - M12 * M12);
+    const float idet = rcp_ftz(M11 * M22 - M12 * M12);
     D.mi11 = M22 * idet; D.mi22 = M11 * idet; D.mi12 = -M12 * idet;
-    D.il11 = rsqrtf(M11); D.l21 = M12 * D.il11; D.il22 = rsqrtf(M22 - D.l21 * D.l21);
+    D.il11 = rsqrt_ftz(M11); D.l21 = M12 * D.il11; D.il22 = rsqrt_ftz(M22 - D.l21 * D.l21);
     const V3 G2f = ant::M_LONG * lam2, G2t = cross(r_fc, G2f) + If_a2;
     const V3 G1fa = ant::M_SHORT * lam1a, G1ff = ant::M_LONG * lam1f;
     const V3 G1f = G1fa + G1ff, G1t = cross(r_ac, G1fa) + ant::IZ_SHORT * a1 + cross(r_fc, G1ff) + If_a1;
@@ -461,7 +457,7 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
         float d = L[j][j];
 #pragma unroll
         for (int kk = 0; kk < j; kk++) d = fmaf(-L[j][kk], L[j][kk], d);
-        rd[j] = rsqrtf(d);
+        rd[j] = rsqrt_ftz(d);
         L[j][j] = d * rd[j];
 #pragma unroll
         for (int i = j + 1; i < 6; i++) {
@@ -508,7 +504,7 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
   }
 
   // ---------------- constraint rows: counts, visit positions, whitened rows ----------------
-  const float inv_h = 1.0f / P.h;
+  const float inv_h = P.inv_h;
   float4* __restrict__ rb = reinterpret_cast<float4*>(rows) + es * HRL_ENV_F4;  // es: this env's slot in the warp
   float* __restrict__ lamp = rows + HRL_ROWS_FLOATS_PER_WARP + es * HRL_LAM_STRIDE;
   const float pl1 = s.q1 - ant::HIP_LO, ph1 = ant::HIP_HI - s.q1;
@@ -642,18 +638,26 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
   s.O = s.O + P.h * s.v;
   s.q1 = fmaf(P.h, u1, s.q1); s.q2 = fmaf(P.h, u2, s.q2);
   {  // q <- exp(w h) * q  (Bullet pQuatUpdateFun with world-frame omega)
-    float ang = norm(s.w);
-    if (ang * P.h > 0.25f * 3.14159265358979323846f) ang = 0.25f * 3.14159265358979323846f / P.h;
-    float kk;
-    if (ang < 0.001f) kk = 0.5f * P.h - P.h * P.h * P.h * 0.020833333333f * ang * ang;
-    else kk = sinf(0.5f * ang * P.h) / ang;
-    const float ax = s.w.x * kk, ay = s.w.y * kk, az = s.w.z * kk, cw = cosf(0.5f * ang * P.h);
+    // half angle y = |w| h / 2: exp = (w * sin(y)/|w|, cos(y)).  Bullet caps |w| h at pi/4, so y <= pi/8
+    // and the even Taylor polynomials in y^2 below are exact to 2e-9 (sinc) / 2e-11 (cos): no sqrt,
+    // no division, no branch.  |w| h > pi/4 (needs max_coord_vel > 110) takes the literal path.
+    const float w2 = dot(s.w, s.w), y2 = 0.25f * P.h * P.h * w2;
+    float kk, cw;
+    if (y2 <= 0.1542126f) {  // (pi/8)^2
+      kk = 0.5f * P.h * fmaf(y2, fmaf(y2, fmaf(y2, fmaf(y2, 2.7557319e-6f, -1.9841270e-4f), 8.3333333e-3f), -0.16666667f), 1.f);
+      cw = fmaf(y2, fmaf(y2, fmaf(y2, fmaf(y2, 2.4801587e-5f, -1.3888889e-3f), 4.1666667e-2f), -0.5f), 1.f);
+    } else {
+      float ang = sqrtf(w2);
+      if (ang * P.h > 0.25f * 3.14159265358979323846f) ang = 0.25f * 3.14159265358979323846f / P.h;
+      kk = sinf(0.5f * ang * P.h) / ang; cw = cosf(0.5f * ang * P.h);
+    }
+    const float ax = s.w.x * kk, ay = s.w.y * kk, az = s.w.z * kk;
     const float x = s.qx, y = s.qy, z = s.qz, qw = s.qw;
     float nx = cw * x + ax * qw + ay * z - az * y;
     float ny = cw * y + ay * qw + az * x - ax * z;
     float nz = cw * z + az * qw + ax * y - ay * x;
     float nw = cw * qw - ax * x - ay * y - az * z;
-    const float inv = rsqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+    const float inv = rsqrt_ftz(nx * nx + ny * ny + nz * nz + nw * nw);
     s.qx = nx * inv; s.qy = ny * inv; s.qz = nz * inv; s.qw = nw * inv;
   }
 }

@@ -41,9 +41,16 @@ struct hrl_handle {
   DevState st;
   float* d_bounds;  // lidar bound lines [7][4]
   int n_lines;
-  // staging for hrl_step_host
+  // staging for hrl_step_host: ONE device block laid out [obs | rew | info | done] so that a host
+  // buffer with the same layout (hrl_host_layout) comes back with a single copy
   float *s_act, *s_obs, *s_rew, *s_info;
   uint8_t* s_done;
+  size_t s_out_bytes;
+  int host_mode;  // HRL_HOST_AUTO / HRL_HOST_COPY / HRL_HOST_ZEROCOPY
+  // small cache of (host pointer -> device alias) so that steady-state steps skip cudaPointerGetAttributes
+  const void* alias_key[12];
+  void* alias_val[12];
+  int alias_n;
 };
 
 static thread_local char g_err[512] = "";
@@ -69,7 +76,8 @@ static int cuda_fail(cudaError_t e, const char* where) {
 __device__ __forceinline__ float clip5(float x) { return fminf(fmaxf(x, -5.f), 5.f); }
 
 // Flagrun goal j of episode ep: ant_flagrun_env.py:71-78; the stream is shared by all envs (:39)
-__device__ __forceinline__ void flag_goal(const hrl_config& cfg, int ep, int j, float& gx, float& gy) {
+// rarely executed: kept out of line so that the hot task-layer code stays compact in the I-cache
+__device__ __noinline__ void flag_goal(const hrl_config& cfg, int ep, int j, float& gx, float& gy) {
   const float half = cfg.flag_size * 0.5f;
   for (uint32_t attempt = 0;; attempt++) {
     float u[4];
@@ -82,7 +90,7 @@ __device__ __forceinline__ void flag_goal(const hrl_config& cfg, int ep, int j, 
 
 // gather_scene.py:52-62: uniform on the (size-1)^2 square, rejected while closer than `spacing`
 // to (ax, ay).  Evaluated in double from 24-bit uniforms and rounded to f32 (bit-identical to the oracle).
-__device__ __forceinline__ void place_item(const hrl_config& cfg, uint32_t genv, uint32_t stream, uint32_t draw,
+__device__ __noinline__ void place_item(const hrl_config& cfg, uint32_t genv, uint32_t stream, uint32_t draw,
                                            int item, float ax, float ay, float& ox, float& oy) {
   const double sx = (double)cfg.world_size[0] - 1.0, sy = (double)cfg.world_size[1] - 1.0;
   for (int attempt = 0;; attempt++) {
@@ -823,6 +831,19 @@ int hrl_obs_dim(const hrl_config* c) {
 }
 int hrl_act_dim(const hrl_config* c) { return !c ? -1 : (c->env_kind == HRL_POINT_GATHER ? 2 : 8); }
 
+int hrl_host_layout(const hrl_config* c, size_t* off_rew, size_t* off_info, size_t* off_done, size_t* total) {
+  if (!c || hrl_obs_dim(c) < 0 || c->num_envs <= 0) return set_err(HRL_E_INVALID, "bad config for hrl_host_layout");
+  const size_t N = (size_t)c->num_envs, D = (size_t)hrl_obs_dim(c);
+  const size_t o_rew = (N * D * sizeof(float) + 255) / 256 * 256;
+  const size_t o_info = o_rew + (N * sizeof(float) + 255) / 256 * 256;
+  const size_t o_done = o_info + N * 4 * sizeof(float);
+  if (off_rew) *off_rew = o_rew;
+  if (off_info) *off_info = o_info;
+  if (off_done) *off_done = o_done;
+  if (total) *total = (o_done + N + 255) / 256 * 256;
+  return HRL_OK;
+}
+
 static int validate(const hrl_config* c) {
   if (!c) return set_err(HRL_E_INVALID, "null config");
   if (c->num_envs <= 0) return set_err(HRL_E_INVALID, "num_envs must be > 0");
@@ -841,7 +862,7 @@ int hrl_destroy(hrl_handle* h) {
   cudaSetDevice(h->device);
   cudaFree(h->st.base); cudaFree(h->st.leg); cudaFree(h->st.items); cudaFree(h->st.miscf); cudaFree(h->st.misci);
   cudaFree(h->st.stats); cudaFree(h->d_bounds);
-  cudaFree(h->s_act); cudaFree(h->s_obs); cudaFree(h->s_rew); cudaFree(h->s_info); cudaFree(h->s_done);
+  cudaFree(h->s_act); cudaFree(h->s_obs);  // s_rew / s_info / s_done live inside the s_obs block
   delete h;
   return HRL_OK;
 }
@@ -874,10 +895,15 @@ int hrl_create(const hrl_config* cfg, int32_t device, hrl_handle** out) {
   ALLOC(h->st.stats, 4 * sizeof(unsigned long long));
   ALLOC(h->d_bounds, 7 * 4 * sizeof(float));
   ALLOC(h->s_act, N * h->A * sizeof(float));
-  ALLOC(h->s_obs, N * h->D * sizeof(float));
-  ALLOC(h->s_rew, N * sizeof(float));
-  ALLOC(h->s_info, N * 4 * sizeof(float));
-  ALLOC(h->s_done, N);
+  {
+    size_t off_rew, off_info, off_done, total;
+    hrl_host_layout(cfg, &off_rew, &off_info, &off_done, &total);
+    ALLOC(h->s_obs, total);
+    h->s_rew = (float*)((char*)h->s_obs + off_rew);
+    h->s_info = (float*)((char*)h->s_obs + off_info);
+    h->s_done = (uint8_t*)h->s_obs + off_done;
+    h->s_out_bytes = total;
+  }
 #undef ALLOC
   float b[28];
   h->n_lines = scene_bounds(cfg, b);
@@ -923,19 +949,63 @@ int hrl_step(hrl_handle* h, const float* d_actions, float* d_obs, float* d_rew, 
   return launch_env(h, 0, 0, d_actions, nullptr, d_obs, d_rew, d_done, d_info, d_terminal_obs, (cudaStream_t)stream);
 }
 
+/* non-NULL when `p` is pinned host memory the device can address directly (UVA): the device alias.
+ * Pinned buffers are long-lived in a stepping loop, so positive answers are cached per handle. */
+static void* mapped_alias(hrl_handle* h, const void* p) {
+  for (int i = 0; i < h->alias_n; i++)
+    if (h->alias_key[i] == p) return h->alias_val[i];
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  void* d = (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
+  if (d) {
+    if (h->alias_n == 12) h->alias_n = 0;  // tiny ring: evict everything
+    h->alias_key[h->alias_n] = p; h->alias_val[h->alias_n] = d; h->alias_n++;
+  }
+  return d;
+}
+
+int hrl_set_host_mode(hrl_handle* h, int32_t mode) {
+  if (!h || mode < HRL_HOST_AUTO || mode > HRL_HOST_ZEROCOPY) return set_err(HRL_E_INVALID, "bad argument to hrl_set_host_mode");
+  h->host_mode = mode;
+  return HRL_OK;
+}
+
 int hrl_step_host(hrl_handle* h, const float* h_actions, float* h_obs, float* h_rew, uint8_t* h_done, float* h_info,
                   void* stream) {
   if (!h || !h_actions || !h_obs || !h_rew || !h_done) return set_err(HRL_E_INVALID, "null argument to hrl_step_host");
   cudaStream_t s = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
   const size_t N = (size_t)h->N;
+  if (h->host_mode != HRL_HOST_COPY) {
+    // zero-copy: the kernel reads the actions from and writes its results to pinned host memory over
+    // PCIe while it computes, so the transfers overlap the step instead of bracketing it
+    float* a = (float*)mapped_alias(h, h_actions);
+    float* o = (float*)mapped_alias(h, h_obs);
+    float* r = (float*)mapped_alias(h, h_rew);
+    uint8_t* d = (uint8_t*)mapped_alias(h, h_done);
+    float* i = h_info ? (float*)mapped_alias(h, h_info) : nullptr;
+    if (a && o && r && d && (i || !h_info)) {
+      int rc = launch_env(h, 0, 0, a, nullptr, o, r, d, i, nullptr, s);
+      if (rc) return rc;
+      CK(cudaStreamSynchronize(s));
+      return HRL_OK;
+    }
+    if (h->host_mode == HRL_HOST_ZEROCOPY) return set_err(HRL_E_INVALID, "zero-copy host mode needs pinned (page-locked) buffers");
+  }
   CK(cudaMemcpyAsync(h->s_act, h_actions, N * h->A * sizeof(float), cudaMemcpyHostToDevice, s));
-  int rc = launch_env(h, 0, 0, h->s_act, nullptr, h->s_obs, h->s_rew, h->s_done, h_info ? h->s_info : nullptr, nullptr, s);
+  int rc = launch_env(h, 0, 0, h->s_act, nullptr, h->s_obs, h->s_rew, h->s_done, h->s_info, nullptr, s);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(h_obs, h->s_obs, N * h->D * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(h_rew, h->s_rew, N * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(h_done, h->s_done, N, cudaMemcpyDeviceToHost, s));
-  if (h_info) CK(cudaMemcpyAsync(h_info, h->s_info, N * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  size_t off_rew, off_info, off_done, total;
+  hrl_host_layout(&h->cfg, &off_rew, &off_info, &off_done, &total);
+  if (h_info && (char*)h_rew == (char*)h_obs + off_rew && (char*)h_info == (char*)h_obs + off_info &&
+      (char*)h_done == (char*)h_obs + off_done) {
+    CK(cudaMemcpyAsync(h_obs, h->s_obs, off_done + N, cudaMemcpyDeviceToHost, s));  // packed layout: one copy
+  } else {
+    CK(cudaMemcpyAsync(h_obs, h->s_obs, N * h->D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_rew, h->s_rew, N * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_done, h->s_done, N, cudaMemcpyDeviceToHost, s));
+    if (h_info) CK(cudaMemcpyAsync(h_info, h->s_info, N * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
   CK(cudaStreamSynchronize(s));
   return HRL_OK;
 }

@@ -21,18 +21,16 @@ __host__ __device__ __forceinline__ double snap_span(float s) {
 // Angle/bin: float32 fast path; when the float result is within 2e-4 of any decision
 // boundary (bin edge, +-half span) the reference's exact float64 sequence is evaluated
 // instead, which makes the bin index bit-exact (SURVEY.md hard part 5).
-__device__ __forceinline__ int gather_item_bin(float rx, float ry, float yaw, float ox, float oy, int n_bins,
-                                               float sensor_range, float span, double* d2_out) {
-  double dxd = __dsub_rn((double)ox, (double)rx), dyd = __dsub_rn((double)oy, (double)ry);
-  double d2 = __dadd_rn(__dmul_rn(dxd, dxd), __dmul_rn(dyd, dyd));
-  *d2_out = d2;
-  if (d2 > (double)sensor_range) return -1;  // :145 (squared distance vs unsquared range, kept)
+// Angle -> bin part, out of line on purpose: one copy instead of one per item keeps the
+// once-per-step task layer small (its cost is instruction fetch, not arithmetic).
+__device__ __noinline__ int gather_angle_bin(double dxd, double dyd, float yaw, int n_bins, float span) {
   float dx = (float)dxd, dy = (float)dyd;
   const float two_pi = 2.0f * HRL_PI_F;
   float a = atan2f(dy, dx) - yaw;  // :148
-  a = fmodf(a, two_pi);
-  if (a < 0.f) a += two_pi;  // Python % semantics :151
-  if (a > HRL_PI_F) a -= two_pi;
+  // Python's `% (2 pi)` then `> pi -> -= 2 pi` (:151-153) == wrap to (-pi, pi]; |a| < 2 pi here
+  // because both atan2 and the Bullet yaw lie in [-pi, pi].  The exact path below keeps fmod.
+  if (a <= -HRL_PI_F) a += two_pi;
+  else if (a > HRL_PI_F) a -= two_pi;
   float half = 0.5f * span, res = span / (float)n_bins;
   float t = (a + half) / res;
   bool risky = fabsf(fabsf(a) - half) < 2e-4f || fabsf(t - rintf(t)) < 2e-4f || !(fabsf(a) < 1e30f);
@@ -53,6 +51,14 @@ __device__ __forceinline__ int gather_item_bin(float rx, float ry, float yaw, fl
   int b = (int)((ad + halfd) / resd);
   // the reference raises IndexError at exactly +half span; clamp instead
   return b > n_bins - 1 ? n_bins - 1 : b;
+}
+__device__ __forceinline__ int gather_item_bin(float rx, float ry, float yaw, float ox, float oy, int n_bins,
+                                               float sensor_range, float span, double* d2_out) {
+  double dxd = __dsub_rn((double)ox, (double)rx), dyd = __dsub_rn((double)oy, (double)ry);
+  double d2 = __dadd_rn(__dmul_rn(dxd, dxd), __dmul_rn(dyd, dyd));
+  *d2_out = d2;
+  if (d2 > (double)sensor_range) return -1;  // :145 (squared distance vs unsquared range, kept)
+  return gather_angle_bin(dxd, dyd, yaw, n_bins, span);
 }
 
 // intersection_utils.py:93-104 (tie order 1,4,2,3)

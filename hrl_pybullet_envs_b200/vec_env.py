@@ -116,20 +116,51 @@ class VecEnv:
             d["terminal_obs"] = term
         return d
 
+    HOST_MODES = {"auto": 0, "copy": 1, "zerocopy": 2}
+
+    def set_host_mode(self, mode):
+        """'zerocopy' (kernel reads/writes pinned host memory over PCIe while it computes), 'copy'
+        (H2D, kernel, one packed D2H) or 'auto' (zero-copy when the buffers are pinned)."""
+        _cabi.check(self.L.hrl_set_host_mode(self.h, self.HOST_MODES[mode]))
+
+    def _host_buffers(self):
+        """Two packed pinned output sets [obs | rew | info | done] (hrl_host_layout) + one action buffer;
+        the sets alternate so that the arrays returned by the previous step stay valid for one more step."""
+        o_rew, o_info, o_done, total = (C.c_size_t() for _ in range(4))
+        _cabi.check(self.L.hrl_host_layout(C.byref(self.cfg), C.byref(o_rew), C.byref(o_info), C.byref(o_done), C.byref(total)))
+        sets = []
+        for _ in range(2):
+            raw = torch.zeros(total.value, dtype=torch.uint8, pin_memory=True)
+            base = raw.data_ptr()
+            v = raw.numpy()
+            sets.append(dict(
+                raw=raw,
+                obs=v[:self.N * self.D * 4].view(np.float32).reshape(self.N, self.D),
+                rew=v[o_rew.value:o_rew.value + self.N * 4].view(np.float32),
+                info=v[o_info.value:o_info.value + self.N * 16].view(np.float32).reshape(self.N, 4),
+                done=v[o_done.value:o_done.value + self.N],
+                p_obs=C.c_void_p(base), p_rew=C.c_void_p(base + o_rew.value), p_info=C.c_void_p(base + o_info.value),
+                p_done=C.c_void_p(base + o_done.value)))
+        act = torch.zeros(self.N, self.A, pin_memory=True)
+        return dict(sets=sets, act=act, act_np=act.numpy(), p_act=C.c_void_p(act.data_ptr()), flip=0)
+
     def step_host(self, actions):
-        """numpy in / numpy out through ``hrl_step_host`` (H2D + kernel + D2H + sync)."""
+        """numpy in / numpy out through ``hrl_step_host``: the call a gym-style user makes.  The
+        returned arrays are views of pinned memory, valid until the step after the next one."""
         if self._host is None:
-            pin = torch.cuda.is_available()
-            self._host = dict(act=torch.zeros(self.N, self.A, pin_memory=pin), obs=torch.zeros(self.N, self.D, pin_memory=pin),
-                              rew=torch.zeros(self.N, pin_memory=pin), done=torch.zeros(self.N, dtype=torch.uint8, pin_memory=pin),
-                              info=torch.zeros(self.N, 4, pin_memory=pin))
+            self._host = self._host_buffers()
         H = self._host
-        H["act"].numpy()[...] = np.asarray(actions, dtype=np.float32).reshape(self.N, self.A)
-        _cabi.check(self.L.hrl_step_host(self.h, _ptr(H["act"]), _ptr(H["obs"]), _ptr(H["rew"]), _ptr(H["done"]),
-                                         _ptr(H["info"]), self._stream()))
-        info = H["info"].numpy()
+        H["act_np"][...] = np.asarray(actions, dtype=np.float32).reshape(self.N, self.A)
+        S = H["sets"][H["flip"]]
+        H["flip"] ^= 1
+        _cabi.check(self.L.hrl_step_host(self.h, H["p_act"], S["p_obs"], S["p_rew"], S["p_done"], S["p_info"], self._stream()))
+        info = S["info"]
         d = {"TimeLimit.truncated": info[:, 2] > 0, "episode_length": info[:, 3]}
-        return H["obs"].numpy(), H["rew"].numpy(), H["done"].numpy().astype(bool), d
+        if self.kind in (HRL_ANT_GATHER, HRL_POINT_GATHER):
+            d["food_rew"] = info[:, 0]; d["dead_rew"] = info[:, 1]
+        else:
+            d["inner_rew"] = info[:, 0]
+        return S["obs"], S["rew"], S["done"].view(np.bool_), d
 
     def observe(self):
         _cabi.check(self.L.hrl_observe(self.h, _ptr(self._obs), self._stream()))

@@ -16,6 +16,7 @@
 #ifndef HRL_B200_H
 #define HRL_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -154,6 +155,21 @@ int hrl_step(hrl_handle* h, const float* d_actions, float* d_obs, float* d_rew, 
  * gym-style user makes with numpy arrays. */
 int hrl_step_host(hrl_handle* h, const float* h_actions, float* h_obs, float* h_rew, uint8_t* h_done,
                   float* h_info, void* stream);
+
+/* How hrl_step_host moves data (the reference has no device boundary: env.step(a) takes and returns
+ * numpy arrays, ant_gather_env.py:76-119, so this is the whole cost of being a drop-in for it):
+ *   HRL_HOST_COPY      H2D copy of the actions, kernel, D2H copies (ONE copy when the four output
+ *                      buffers are carved out of one allocation as hrl_host_layout says), sync;
+ *   HRL_HOST_ZEROCOPY  every buffer must be pinned: the kernel reads / writes them over PCIe while
+ *                      it computes (transfers overlap the step), sync;
+ *   HRL_HOST_AUTO      zero-copy when all buffers are pinned, else copy (default). */
+#define HRL_HOST_AUTO 0
+#define HRL_HOST_COPY 1
+#define HRL_HOST_ZEROCOPY 2
+int hrl_set_host_mode(hrl_handle* h, int32_t mode);
+/* Byte offsets of rew / info / done inside one packed host allocation that starts with obs
+ * (obs f32[N,D] | rew f32[N] | info f32[N,4] | done u8[N], 256-byte aligned sections); total bytes. */
+int hrl_host_layout(const hrl_config* cfg, size_t* off_rew, size_t* off_info, size_t* off_done, size_t* total);
 
 /* Replaces saveState/restoreState (used as the reset mechanism by pybullet_envs) and gives
  * the "identical saved states" hook the one-step parity tests need.

@@ -259,18 +259,44 @@ def test_time_limit_and_auto_reset():
     assert (i[:, K.SI_T] == 0).all() and (i[:, K.SI_EPISODE] == 2).all()
 
 
-def test_step_host_matches_device_path():
+@pytest.mark.parametrize("mode", ["zerocopy", "copy", "auto"])
+def test_step_host_matches_device_path(mode):
+    """hrl_step_host (numpy in/out) in every transfer mode == the device-pointer path, bit for bit."""
     from hrl_pybullet_envs_b200 import VecEnv
     N = 256
     a = VecEnv("AntGatherBulletEnv-v0", N, seed=9); b = VecEnv("AntGatherBulletEnv-v0", N, seed=9)
+    b.set_host_mode(mode)
     a.reset(); b.reset()
     rng = np.random.default_rng(0)
-    for t in range(5):
+    prev = None
+    for t in range(6):
         act = rng.uniform(-1, 1, (N, 8)).astype(np.float32)
-        o1, r1, d1, _ = a.step(torch.tensor(act).cuda())
-        o2, r2, d2, _ = b.step(act)  # numpy in -> hrl_step_host
+        o1, r1, d1, i1 = a.step(torch.tensor(act).cuda())
+        o2, r2, d2, i2 = b.step(act)  # numpy in -> hrl_step_host
         assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
         assert np.array_equal(d1.cpu().numpy(), d2)
+        assert np.array_equal(i1["food_rew"].cpu().numpy(), i2["food_rew"])
+        if prev is not None:  # the arrays of the previous step are still intact (double buffering)
+            assert np.array_equal(prev[0], prev[1])
+        prev = (o2, o2.copy())
+
+
+def test_step_host_pageable_buffers_fall_back_to_copy():
+    """Plain (pageable) numpy buffers through the raw C-ABI: AUTO copies, ZEROCOPY refuses loudly."""
+    import ctypes as C
+    from hrl_pybullet_envs_b200 import VecEnv, _cabi
+    N = 64
+    a = VecEnv("AntGatherBulletEnv-v0", N, seed=2); b = VecEnv("AntGatherBulletEnv-v0", N, seed=2)
+    a.reset(); b.reset()
+    act = np.random.default_rng(1).uniform(-1, 1, (N, 8)).astype(np.float32)
+    obs = np.zeros((N, 46), np.float32); rew = np.zeros(N, np.float32); done = np.zeros(N, np.uint8); info = np.zeros((N, 4), np.float32)
+    P = lambda x: C.c_void_p(x.ctypes.data)
+    _cabi.check(b.L.hrl_step_host(b.h, P(act), P(obs), P(rew), P(done), P(info), b._stream()))
+    o1, r1, d1, _ = a.step(torch.tensor(act).cuda())
+    assert np.array_equal(o1.cpu().numpy(), obs) and np.array_equal(r1.cpu().numpy(), rew)
+    b.set_host_mode("zerocopy")
+    rc = b.L.hrl_step_host(b.h, P(act), P(obs), P(rew), P(done), P(info), b._stream())
+    assert rc != 0 and b"pinned" in b.L.hrl_last_error()
 
 
 def test_gym_surface():
