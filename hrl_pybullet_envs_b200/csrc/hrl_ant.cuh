@@ -228,11 +228,11 @@ __device__ __forceinline__ Row ld_row(const float4* __restrict__ rb, int r) {
   return R;
 }
 __device__ __forceinline__ float dot14(const float2 a[7], const float2 b[7]) {
-  float2 s0 = mul2(a[0], b[0]), s1 = mul2(a[1], b[1]);
-  s0 = fma2(a[2], b[2], s0); s1 = fma2(a[3], b[3], s1);
-  s0 = fma2(a[4], b[4], s0); s1 = fma2(a[5], b[5], s1);
+  // three packed accumulators: dependent depth mul, fma, fma, add2, add2, add
+  float2 s0 = mul2(a[0], b[0]), s1 = mul2(a[1], b[1]), s2 = mul2(a[2], b[2]);
+  s0 = fma2(a[3], b[3], s0); s1 = fma2(a[4], b[4], s1); s2 = fma2(a[5], b[5], s2);
   s0 = fma2(a[6], b[6], s0);
-  const float2 t = add2(s0, s1);
+  const float2 t = add2(add2(s0, s1), s2);
   return t.x + t.y;
 }
 __device__ __forceinline__ void axpy14(float2 y[7], const float2 a[7], float s) {
@@ -568,18 +568,21 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
 #define HRL_NRM_ROW(t) (((t) < NC) ? HRL_ROW_NRM0 + (t) : HRL_ROW_IDLE)
 #define HRL_FRI_ROW(t) (((t) < NC) ? HRL_ROW_FRI0 + 2 * (t) : HRL_ROW_IDLE - 1)
   for (int it = 0; it < P.iters; it++) {
-    // (1) joint-limit rows; Bullet walks the non-contact rows backwards on even iterations
+    // (1) joint-limit rows; Bullet walks the non-contact rows backwards on even iterations.
+    // Two visits per trip (ping-pong row registers, next row prefetched), odd tail handled apart.
     if (maxNL > 0) {
       const int lbase = (it & 1) ? 0 : NL - 1, lstep = (it & 1) ? 1 : -1;
       int r0 = HRL_LIM_ROW(0), r1;
       Row R0 = ld_row(rb, r0), R1;
       float l0 = lamp[r0], l1;
-      for (int t = 0; t < maxNL; t += 2) {
+      int t = 0;
+      for (; t + 1 < maxNL; t += 2) {
         r1 = HRL_LIM_ROW(t + 1); R1 = ld_row(rb, r1); l1 = lamp[r1];
         single_visit<true>(lamp, dv, R0, l0, r0, P.max_imp);
         r0 = HRL_LIM_ROW(t + 2); R0 = ld_row(rb, r0); l0 = lamp[r0];
         single_visit<true>(lamp, dv, R1, l1, r1, P.max_imp);
       }
+      if (t < maxNL) single_visit<true>(lamp, dv, R0, l0, r0, P.max_imp);
     }
     if (maxNC > 0) {
       // (2) contact normals
@@ -587,19 +590,22 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
         int r0 = HRL_NRM_ROW(0), r1;
         Row R0 = ld_row(rb, r0), R1;
         float l0 = lamp[r0], l1;
-        for (int t = 0; t < maxNC; t += 2) {
+        int t = 0;
+        for (; t + 1 < maxNC; t += 2) {
           r1 = HRL_NRM_ROW(t + 1); R1 = ld_row(rb, r1); l1 = lamp[r1];
           single_visit<false>(lamp, dv, R0, l0, r0, 0.f);
           r0 = HRL_NRM_ROW(t + 2); R0 = ld_row(rb, r0); l0 = lamp[r0];
           single_visit<false>(lamp, dv, R1, l1, r1, 0.f);
         }
+        if (t < maxNC) single_visit<false>(lamp, dv, R0, l0, r0, 0.f);
       }
       // (3) friction pairs
       {
         int r0 = HRL_FRI_ROW(0), r1;
         Row A0 = ld_row(rb, r0), B0 = ld_row(rb, r0 + 1), A1, B1;
         float n0 = lamp[HRL_NRM_ROW(0)], a0 = lamp[r0], b0 = lamp[r0 + 1], n1, a1, b1;
-        for (int t = 0; t < maxNC; t += 2) {
+        int t = 0;
+        for (; t + 1 < maxNC; t += 2) {
           r1 = HRL_FRI_ROW(t + 1); A1 = ld_row(rb, r1); B1 = ld_row(rb, r1 + 1);
           n1 = lamp[HRL_NRM_ROW(t + 1)]; a1 = lamp[r1]; b1 = lamp[r1 + 1];
           pair_visit(lamp, dv, A0, B0, n0, a0, b0, r0, P.mu);
@@ -607,6 +613,7 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
           n0 = lamp[HRL_NRM_ROW(t + 2)]; a0 = lamp[r0]; b0 = lamp[r0 + 1];
           pair_visit(lamp, dv, A1, B1, n1, a1, b1, r1, P.mu);
         }
+        if (t < maxNC) pair_visit(lamp, dv, A0, B0, n0, a0, b0, r0, P.mu);
       }
     }
   }

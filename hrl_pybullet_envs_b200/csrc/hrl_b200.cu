@@ -248,11 +248,9 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
     if (!__any_sync(HRL_FULL_MASK, todo != 0)) break;
 
     // ---------------- calc_state of the current register state ----------------
-    float roll, pitch, yaw;
-    quat_to_rpy(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);
-    float sy_, cy_;
-    sincosf(-yaw, &sy_, &cy_);
-    const float vbx = cy_ * s.v.x - sy_ * s.v.y, vby = sy_ * s.v.x + cy_ * s.v.y;
+    float roll, pitch, yaw, cyw, syw;
+    quat_to_rpy(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw, cyw, syw);
+    const float vbx = cyw * s.v.x + syw * s.v.y, vby = cyw * s.v.y - syw * s.v.x;  // Rz(-yaw) v
     const float o_z = clip5(s.O.z - T.initial_z);
     const float o_v0 = clip5(0.3f * vbx), o_v1 = clip5(0.3f * vby), o_v2 = clip5(0.3f * s.v.z);
     const float o_r = clip5(roll), o_p = clip5(pitch);
@@ -270,7 +268,11 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       const float bx = sx * inv_np, by = sy * inv_np;
       const float dx = T.tx - bx, dy = T.ty - by;
       wtd_new = sqrtf(dx * dx + dy * dy);
-      sincosf(atan2f(dy, dx) - yaw, &sin_t, &cos_t);
+      // sin / cos of (atan2(dy, dx) - yaw) by rotating the unit target direction with Rz(-yaw)
+      if (wtd_new > 0.f) {
+        const float iw = 1.0f / wtd_new;
+        cos_t = (dx * cyw + dy * syw) * iw; sin_t = (dy * cyw - dx * syw) * iw;
+      } else { cos_t = cyw; sin_t = -syw; }
     }
     float* so = sobs + es * D;  // dense staging: the warp's observations are one contiguous span
     const bool commit = (todo == 1);

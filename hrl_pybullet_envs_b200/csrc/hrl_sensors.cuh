@@ -27,10 +27,10 @@ __device__ __noinline__ int gather_angle_bin(double dxd, double dyd, float yaw, 
   float dx = (float)dxd, dy = (float)dyd;
   const float two_pi = 2.0f * HRL_PI_F;
   float a = atan2f(dy, dx) - yaw;  // :148
-  // Python's `% (2 pi)` then `> pi -> -= 2 pi` (:151-153) == wrap to (-pi, pi]; |a| < 2 pi here
-  // because both atan2 and the Bullet yaw lie in [-pi, pi].  The exact path below keeps fmod.
-  if (a <= -HRL_PI_F) a += two_pi;
-  else if (a > HRL_PI_F) a -= two_pi;
+  // Python's `% (2 pi)` then `> pi -> -= 2 pi` (:151-153) == wrap to (-pi, pi].  Nearest-multiple
+  // reduction handles any |a| (the gimbal branch of the Bullet yaw reaches +-2 pi); the two forms only
+  // differ at |a| = pi, which is either outside the half span or "risky" and re-evaluated exactly below.
+  a = fmaf(-two_pi, rintf(a * (1.0f / two_pi)), a);
   float half = 0.5f * span, res = span / (float)n_bins;
   float t = (a + half) / res;
   bool risky = fabsf(fabsf(a) - half) < 2e-4f || fabsf(t - rintf(t)) < 2e-4f || !(fabsf(a) < 1e30f);
@@ -103,14 +103,20 @@ __device__ __forceinline__ float lidar_ray(int i, int n_bins, float span_f, floa
   return (float)best;
 }
 
-// Bullet getEulerFromQuaternion (SURVEY.md A.3 "Queries")
-__device__ __forceinline__ void quat_to_rpy(float x, float y, float z, float w, float& roll, float& pitch, float& yaw) {
+// Bullet getEulerFromQuaternion (SURVEY.md A.3 "Queries").  Also returns cos/sin of the yaw: outside
+// the gimbal branch they follow from the atan2 arguments with one rsqrt (no sincos evaluation).
+__device__ __forceinline__ void quat_to_rpy(float x, float y, float z, float w, float& roll, float& pitch, float& yaw,
+                                            float& cyaw, float& syaw) {
   float sarg = -2.f * (x * z - w * y);
-  if (sarg <= -0.99999f) { pitch = -0.5f * HRL_PI_F; roll = 0.f; yaw = 2.f * atan2f(x, -y); }
-  else if (sarg >= 0.99999f) { pitch = 0.5f * HRL_PI_F; roll = 0.f; yaw = 2.f * atan2f(-x, y); }
+  if (sarg <= -0.99999f) { pitch = -0.5f * HRL_PI_F; roll = 0.f; yaw = 2.f * atan2f(x, -y); sincosf(yaw, &syaw, &cyaw); }
+  else if (sarg >= 0.99999f) { pitch = 0.5f * HRL_PI_F; roll = 0.f; yaw = 2.f * atan2f(-x, y); sincosf(yaw, &syaw, &cyaw); }
   else {
     pitch = asinf(sarg);
     roll = atan2f(2.f * (y * z + w * x), w * w - x * x - y * y + z * z);
-    yaw = atan2f(2.f * (x * y + w * z), w * w + x * x - y * y - z * z);
+    const float ys = 2.f * (x * y + w * z), yc = w * w + x * x - y * y - z * z;
+    yaw = atan2f(ys, yc);
+    const float h2 = ys * ys + yc * yc;
+    if (h2 > 0.f) { const float ih = rsqrt_ftz(h2); cyaw = yc * ih; syaw = ys * ih; }
+    else { cyaw = 1.f; syaw = 0.f; }  // atan2(0, 0) = 0
   }
 }

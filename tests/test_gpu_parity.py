@@ -115,6 +115,7 @@ def test_one_step_parity(env_id):
     checked = 0
     worst_p = worst_v = worst_r = worst_o = 0.0
     n_out = 0
+    sens_bad = sens_n = 0
     out_near, out_ev, out_ep = [], [], []
     for t in range(T):
         a = (torch.rand(N, g.A, generator=gen) * 2 - 1)
@@ -145,7 +146,14 @@ def test_one_step_parity(env_id):
             # reward tolerance scales with |reward| for the progress term (1/dt amplification of 1e-3 m is 0.06)
             if env_id in ("AntGatherBulletEnv-v0", "PointGatherBulletEnv-v0", "AntMazeBulletEnv-v0", "AntMazeMjEnv-v0"):
                 assert np.abs(rg[idx] - ro[idx]).max(initial=0) <= REW_TOL
-            worst_o = max(worst_o, float(np.abs(og[idx] - oo[idx]).max(initial=0)))
+            # Gather: the sector readings are a discontinuous function of the pose (an item on a bin edge
+            # moves to the next bin for a 1e-7 rad yaw difference), so inside the physics tolerance only the
+            # continuous part of the observation is held to a tolerance here; bin-exactness on IDENTICAL poses
+            # is what test_gather_sensor_* pins.  Flipped readings must stay rare.
+            nsm = 26 if env_id == "AntGatherBulletEnv-v0" else (8 if env_id == "PointGatherBulletEnv-v0" else og.shape[1])
+            worst_o = max(worst_o, float(np.abs(og[idx, :nsm] - oo[idx, :nsm]).max(initial=0)))
+            if nsm < og.shape[1] and len(idx):
+                sens_bad += int((np.abs(og[idx, nsm:] - oo[idx, nsm:]) > 2e-3).sum()); sens_n += og[idx, nsm:].size
             # finished envs: terminal obs agree and both reset to the same new episode
             fin = same & dg
             if fin.any():
@@ -166,6 +174,7 @@ def test_one_step_parity(env_id):
         assert max(out_ev) < 3.0 and max(out_ep) < 2e-2  # one sub-step of un-stopped joint acceleration at most
     assert frac < 5e-3, (n_out, checked)
     assert worst_o < 2e-2
+    assert sens_bad <= 2e-4 * max(sens_n, 1), (sens_bad, sens_n)
 
 
 @pytest.mark.parametrize("env_id", ["AntGatherBulletEnv-v0", "AntMazeBulletEnv-v0"])
