@@ -33,6 +33,12 @@ struct DevState {
   float4* miscf;  // [N][2]: (target.x, target.y, -, -) (feet0..3)
   int4* misci;    // [N][2]: (t, episode, steps_total, goals_left) (since, rewarded, -, -)
   unsigned long long* stats;  // [4]: contacts, limit rows, env-substeps, non-finite resets
+  // completion signal of the zero-copy host path: the last CTA to finish writes fin_seq to the
+  // pinned host word fin_flag (NULL: no signalling), so the host can poll instead of paying a
+  // driver-level stream synchronisation
+  unsigned int* fin_count;
+  unsigned int* fin_flag;
+  unsigned int fin_seq;
 };
 
 struct hrl_handle {
@@ -47,6 +53,8 @@ struct hrl_handle {
   uint8_t* s_done;
   size_t s_out_bytes;
   int host_mode;  // HRL_HOST_AUTO / HRL_HOST_COPY / HRL_HOST_ZEROCOPY
+  unsigned int* h_flag;  // pinned host word polled by hrl_step_host (zero-copy mode)
+  unsigned int seq;
   // small cache of (host pointer -> device alias) so that steady-state steps skip cudaPointerGetAttributes
   const void* alias_key[12];
   void* alias_val[12];
@@ -504,6 +512,21 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       }
     }
   }
+  if (st.fin_flag) {
+    // release at device scope by every writer; the last CTA acquires through the counter and then
+    // publishes with a system-scope fence (fences are cumulative; PCIe posted writes stay ordered)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned prev = atomicAdd(st.fin_count, 1u);
+      if (prev == gridDim.x - 1) {  // last CTA: all others fenced before they counted
+        __threadfence();
+        *st.fin_count = 0;
+        __threadfence_system();
+        *(volatile unsigned int*)st.fin_flag = st.fin_seq;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -863,7 +886,8 @@ int hrl_destroy(hrl_handle* h) {
   if (!h) return HRL_OK;
   cudaSetDevice(h->device);
   cudaFree(h->st.base); cudaFree(h->st.leg); cudaFree(h->st.items); cudaFree(h->st.miscf); cudaFree(h->st.misci);
-  cudaFree(h->st.stats); cudaFree(h->d_bounds);
+  cudaFree(h->st.stats); cudaFree(h->d_bounds); cudaFree(h->st.fin_count);
+  if (h->h_flag) cudaFreeHost(h->h_flag);
   cudaFree(h->s_act); cudaFree(h->s_obs);  // s_rew / s_info / s_done live inside the s_obs block
   delete h;
   return HRL_OK;
@@ -895,6 +919,9 @@ int hrl_create(const hrl_config* cfg, int32_t device, hrl_handle** out) {
   ALLOC(h->st.miscf, N * 2 * sizeof(float4));
   ALLOC(h->st.misci, N * 2 * sizeof(int4));
   ALLOC(h->st.stats, 4 * sizeof(unsigned long long));
+  ALLOC(h->st.fin_count, sizeof(unsigned int));
+  if (cudaHostAlloc((void**)&h->h_flag, 64, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); h->h_flag = nullptr; }
+  else *h->h_flag = 0;
   ALLOC(h->d_bounds, 7 * 4 * sizeof(float));
   ALLOC(h->s_act, N * h->A * sizeof(float));
   {
@@ -922,8 +949,15 @@ int hrl_create(const hrl_config* cfg, int32_t device, hrl_handle** out) {
 }
 
 static int launch_env(hrl_handle* h, int mode, int n_sub, const float* act, const uint8_t* mask, float* obs, float* rew,
-                      uint8_t* done, float* info, float* term, cudaStream_t s) {
+                      uint8_t* done, float* info, float* term, cudaStream_t s, bool signal = false) {
   CK(cudaSetDevice(h->device));
+  DevState st = h->st;
+  st.fin_flag = nullptr;
+  if (signal && h->h_flag && h->cfg.env_kind != HRL_POINT_GATHER) {
+    void* dflag = nullptr;
+    if (cudaHostGetDevicePointer(&dflag, h->h_flag, 0) == cudaSuccess) { st.fin_flag = (unsigned int*)dflag; st.fin_seq = ++h->seq; }
+    else cudaGetLastError();
+  }
   if (h->cfg.env_kind == HRL_POINT_GATHER) {
     const int B = 128, G = (h->N + B - 1) / B;
     point_env_kernel<<<G, B, 0, s>>>(h->cfg, h->st, act, mask, obs, rew, done, info, term, mode, n_sub, h->D);
@@ -931,12 +965,29 @@ static int launch_env(hrl_handle* h, int mode, int n_sub, const float* act, cons
     const int T = 32 * HRL_WARPS_PER_CTA, EPC = HRL_EPW * HRL_WARPS_PER_CTA, G = (h->N + EPC - 1) / EPC;
     const size_t smem = (size_t)HRL_WARPS_PER_CTA * SMEM_PER_WARP_FLOATS * sizeof(float);
     if (h->cfg.env_kind == HRL_ANT_GATHER)
-      ant_env_kernel<0><<<G, T, smem, s>>>(h->cfg, h->st, h->d_bounds, h->n_lines, act, mask, obs, rew, done, info, term, mode, n_sub, h->D);
+      ant_env_kernel<0><<<G, T, smem, s>>>(h->cfg, st, h->d_bounds, h->n_lines, act, mask, obs, rew, done, info, term, mode, n_sub, h->D);
     else
-      ant_env_kernel<1><<<G, T, smem, s>>>(h->cfg, h->st, h->d_bounds, h->n_lines, act, mask, obs, rew, done, info, term, mode, n_sub, h->D);
+      ant_env_kernel<1><<<G, T, smem, s>>>(h->cfg, st, h->d_bounds, h->n_lines, act, mask, obs, rew, done, info, term, mode, n_sub, h->D);
   }
   g_launches++;
   CK(cudaGetLastError());
+  if (st.fin_flag) {
+    // poll the completion word (written after a system-scope fence by the last CTA); look at the
+    // stream now and then so that a failed launch cannot hang the caller
+    volatile unsigned int* f = h->h_flag;
+    for (unsigned spins = 1; *f != st.fin_seq; spins++) {
+      if ((spins & 0x3fff) == 0) {
+        cudaError_t q = cudaStreamQuery(s);
+        if (q == cudaErrorNotReady) continue;
+        if (q != cudaSuccess) return cuda_fail(q, "env kernel");
+        break;  // stream drained: results are visible
+      }
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  }
   return HRL_OK;
 }
 
@@ -987,9 +1038,10 @@ int hrl_step_host(hrl_handle* h, const float* h_actions, float* h_obs, float* h_
     uint8_t* d = (uint8_t*)mapped_alias(h, h_done);
     float* i = h_info ? (float*)mapped_alias(h, h_info) : nullptr;
     if (a && o && r && d && (i || !h_info)) {
-      int rc = launch_env(h, 0, 0, a, nullptr, o, r, d, i, nullptr, s);
+      const bool poll = h->h_flag && h->cfg.env_kind != HRL_POINT_GATHER;
+      int rc = launch_env(h, 0, 0, a, nullptr, o, r, d, i, nullptr, s, poll);
       if (rc) return rc;
-      CK(cudaStreamSynchronize(s));
+      if (!poll) CK(cudaStreamSynchronize(s));
       return HRL_OK;
     }
     if (h->host_mode == HRL_HOST_ZEROCOPY) return set_err(HRL_E_INVALID, "zero-copy host mode needs pinned (page-locked) buffers");

@@ -4,6 +4,7 @@ Host-side mirror of the reference's gym surface for N envs at once.  All arithme
 the sm_100a kernels behind the C-ABI (``_cabi``); torch only supplies device memory and streams.
 """
 import ctypes as C
+from collections.abc import Mapping
 
 import numpy as np
 import torch
@@ -14,6 +15,44 @@ from .config import (ENV_IDS, HRL_STATE_F, HRL_STATE_I, HRL_ANT_FLAGRUN, HRL_ANT
 
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class LazyInfo(Mapping):
+    """The step's ``info`` as a read-only mapping over the raw ``info[N, 4]`` array the kernel wrote
+    (food_rew | inner reward, dead_rew | goals_left, TimeLimit.truncated, episode length).  Entries
+    are materialised on access, so a stepping loop that never looks at ``info`` launches nothing
+    besides the env kernel.  Keys follow the reference: ant_gather_env.py:119 ('food_rew',
+    'dead_rew'), gym TimeLimit ('TimeLimit.truncated')."""
+
+    def __init__(self, raw, kind, term=None):
+        self.raw, self._kind, self._term = raw, kind, term
+        keys = ["TimeLimit.truncated", "episode_length"]
+        keys += ["food_rew", "dead_rew"] if kind in (HRL_ANT_GATHER, HRL_POINT_GATHER) else ["inner_rew"]
+        if kind == HRL_ANT_FLAGRUN:
+            keys.append("goals_left")
+        if term is not None:
+            keys.append("terminal_obs")
+        self._keys = keys
+
+    def __getitem__(self, k):
+        if k not in self._keys:
+            raise KeyError(k)
+        r = self.raw
+        if k == "TimeLimit.truncated":
+            return r[:, 2] > 0
+        if k == "episode_length":
+            return r[:, 3]
+        if k in ("food_rew", "inner_rew"):
+            return r[:, 0]
+        if k in ("dead_rew", "goals_left"):
+            return r[:, 1]
+        return self._term
+
+    def __iter__(self):
+        return iter(self._keys)
+
+    def __len__(self):
+        return len(self._keys)
 
 
 class VecEnv:
@@ -101,20 +140,10 @@ class VecEnv:
             term = self._term
         _cabi.check(self.L.hrl_step(self.h, _ptr(a), _ptr(self._obs), _ptr(self._rew), _ptr(self._done),
                                     _ptr(self._info), _ptr(term), self._stream()))
-        return self._obs, self._rew, self._done.bool(), self._info_dict(self._info, term)
+        return self._obs, self._rew, self._done.view(torch.bool), self._info_dict(self._info, term)
 
     def _info_dict(self, info, term=None):
-        d = {"TimeLimit.truncated": info[:, 2] > 0, "episode_length": info[:, 3]}
-        if self.kind in (HRL_ANT_GATHER, HRL_POINT_GATHER):
-            d["food_rew"] = info[:, 0]   # ant_gather_env.py:119
-            d["dead_rew"] = info[:, 1]
-        else:
-            d["inner_rew"] = info[:, 0]
-            if self.kind == HRL_ANT_FLAGRUN:
-                d["goals_left"] = info[:, 1]
-        if term is not None:
-            d["terminal_obs"] = term
-        return d
+        return LazyInfo(info, self.kind, term)
 
     HOST_MODES = {"auto": 0, "copy": 1, "zerocopy": 2}
 
@@ -138,9 +167,12 @@ class VecEnv:
                 obs=v[:self.N * self.D * 4].view(np.float32).reshape(self.N, self.D),
                 rew=v[o_rew.value:o_rew.value + self.N * 4].view(np.float32),
                 info=v[o_info.value:o_info.value + self.N * 16].view(np.float32).reshape(self.N, 4),
-                done=v[o_done.value:o_done.value + self.N],
+                done=v[o_done.value:o_done.value + self.N].view(np.bool_),
                 p_obs=C.c_void_p(base), p_rew=C.c_void_p(base + o_rew.value), p_info=C.c_void_p(base + o_info.value),
                 p_done=C.c_void_p(base + o_done.value)))
+        for S in sets:
+            S["info_map"] = LazyInfo(S["info"], self.kind)
+            S["ret"] = (S["obs"], S["rew"], S["done"], S["info_map"])
         act = torch.zeros(self.N, self.A, pin_memory=True)
         return dict(sets=sets, act=act, act_np=act.numpy(), p_act=C.c_void_p(act.data_ptr()), flip=0)
 
@@ -150,17 +182,13 @@ class VecEnv:
         if self._host is None:
             self._host = self._host_buffers()
         H = self._host
-        H["act_np"][...] = np.asarray(actions, dtype=np.float32).reshape(self.N, self.A)
+        np.copyto(H["act_np"], np.asarray(actions).reshape(self.N, self.A), casting="same_kind")
         S = H["sets"][H["flip"]]
         H["flip"] ^= 1
-        _cabi.check(self.L.hrl_step_host(self.h, H["p_act"], S["p_obs"], S["p_rew"], S["p_done"], S["p_info"], self._stream()))
-        info = S["info"]
-        d = {"TimeLimit.truncated": info[:, 2] > 0, "episode_length": info[:, 3]}
-        if self.kind in (HRL_ANT_GATHER, HRL_POINT_GATHER):
-            d["food_rew"] = info[:, 0]; d["dead_rew"] = info[:, 1]
-        else:
-            d["inner_rew"] = info[:, 0]
-        return S["obs"], S["rew"], S["done"].view(np.bool_), d
+        rc = self.L.hrl_step_host(self.h, H["p_act"], S["p_obs"], S["p_rew"], S["p_done"], S["p_info"], self._stream())
+        if rc:
+            _cabi.check(rc)
+        return S["ret"]
 
     def observe(self):
         _cabi.check(self.L.hrl_observe(self.h, _ptr(self._obs), self._stream()))
