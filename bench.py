@@ -31,6 +31,16 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/dram_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    try:
+        return json.load(open(p))["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -262,7 +272,8 @@ def run_ours(args):
             "episode_stats": {"episodes_started": episodes, "env_steps_total": env_steps},
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": roofline.BYTES_PER_ENV_STEP * N / launch_s / 1e9, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": roofline.BYTES_PER_ENV_STEP * N / launch_s / 1e9 / hbm_peak, "traffic": None,
+                         "unit": "GB/s", "frac": roofline.BYTES_PER_ENV_STEP * N / launch_s / 1e9 / hbm_peak,
+                         "traffic": ncu_traffic() if N == ENVS_PER_GPU else None,
                          "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
                          "note": "state traffic is not the binding resource; see roofline_fp32"},
             "roofline_fp32": {"bound": "fp32", "achieved": flops * N / launch_s / 1e12, "peak": roofline.fp32_peak_tflops(sm_max),
