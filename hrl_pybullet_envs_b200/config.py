@@ -44,6 +44,8 @@ class HrlConfig(C.Structure):
         ("sense_walls", C.c_int32), ("flag_max_targets", C.c_int32), ("flag_timeout", C.c_int32),
         ("flag_size", C.c_float), ("goal_reach_rew", C.c_float), ("flag_seed", C.c_uint64),
         ("electricity_cost", C.c_float), ("stall_torque_cost", C.c_float), ("joints_at_limit_cost", C.c_float),
+        ("sense_target", C.c_int32), ("maze_max_steps", C.c_int32), ("targ_dist_rew", C.c_int32),
+        ("flag_use_sensor", C.c_int32), ("flag_switch_on_collision", C.c_int32), ("flag_max_target_dist", C.c_float),
     ]
 
     def copy(self):
@@ -89,7 +91,8 @@ def apply_kwargs(cfg, kind, kw):
         if "respawn" in kw:
             cfg.respawn = int(bool(kw.pop("respawn")))
         if "use_sensor" in kw:
-            if not kw.pop("use_sensor"):
+            cfg.use_sensor = int(bool(kw.pop("use_sensor")))  # False: get_abs_pos, ant_gather_env.py:179-196
+            if not cfg.use_sensor and kind == HRL_POINT_GATHER:
                 raise NotImplementedError(_UNSUPPORTED % ("use_sensor", False))
         if cfg.robot_coll_dist <= 0:
             raise NotImplementedError(_UNSUPPORTED % ("robot_coll_dist", cfg.robot_coll_dist))
@@ -123,10 +126,12 @@ def apply_kwargs(cfg, kind, kw):
                 cfg.sense_walls = int(bool(kw.pop("sense_walls")))
             if "done_at_target" in kw:
                 cfg.done_at_target = int(bool(kw.pop("done_at_target")))
-            for name, default in (("sense_target", False), ("max_steps", -1), ("targ_dist_rew", False)):
-                if name in kw and kw[name] != default:
-                    raise NotImplementedError(_UNSUPPORTED % (name, kw[name]))
-                kw.pop(name, None)
+            if "sense_target" in kw:
+                cfg.sense_target = int(bool(kw.pop("sense_target")))
+            if "max_steps" in kw:
+                cfg.maze_max_steps = int(kw.pop("max_steps"))
+            if "targ_dist_rew" in kw:
+                cfg.targ_dist_rew = int(bool(kw.pop("targ_dist_rew")))
     elif kind == HRL_ANT_FLAGRUN:
         if "size" in kw:
             cfg.flag_size = float(kw.pop("size"))
@@ -140,13 +145,26 @@ def apply_kwargs(cfg, kind, kw):
             cfg.flag_timeout = int(kw.pop("timeout"))
         if "seed" in kw:
             cfg.flag_seed = int(kw.pop("seed"))
-        for name, default in (("max_target_dist", 0), ("enclosed", True), ("use_sensor", False),
-                              ("switch_flag_on_collision", True), ("manual_goal_creation", False)):
+        if "max_target_dist" in kw:
+            cfg.flag_max_target_dist = float(kw.pop("max_target_dist"))
+        # ant_flagrun_env.py:17-18: exactly one of max_targets / max_target_dist drives the goals
+        if not ((cfg.flag_max_target_dist == 0 and cfg.flag_max_targets > 0) or
+                (cfg.flag_max_targets <= 0 and cfg.flag_max_target_dist > 0)):
+            raise AssertionError("cannot have both max_targets and max_target_dist set at the same time")
+        if "use_sensor" in kw:
+            cfg.flag_use_sensor = int(bool(kw.pop("use_sensor")))
+        if "switch_flag_on_collision" in kw:
+            cfg.flag_switch_on_collision = int(bool(kw.pop("switch_flag_on_collision")))
+        if "sensor_bins" in kw:
+            cfg.n_bins = int(kw.pop("sensor_bins"))
+        if "sensor_span" in kw:
+            cfg.sensor_span = float(kw.pop("sensor_span"))
+        if "sensor_range" in kw:
+            cfg.sensor_range = float(kw.pop("sensor_range"))
+        for name, default in (("enclosed", True), ("manual_goal_creation", False)):
             if name in kw and kw[name] != default:
                 raise NotImplementedError(_UNSUPPORTED % (name, kw[name]))
             kw.pop(name, None)
-        for name in ("sensor_bins", "sensor_span", "sensor_range"):
-            kw.pop(name, None)  # only read when use_sensor=True
         if cfg.flag_max_targets > 127:
             raise ValueError("max_targets must be <= 127")
     if kw:
@@ -158,11 +176,18 @@ def apply_kwargs(cfg, kind, kw):
     return cfg
 
 
+def food_obs_dim(cfg):
+    if cfg.use_sensor:
+        return 2 * cfg.n_bins
+    return 2 * min(cfg.n_bins, cfg.n_food) + 2 * min(cfg.n_bins, cfg.n_poison)
+
+
 def obs_dim(cfg):
     k = cfg.env_kind
-    return {HRL_ANT_GATHER: 26 + 2 * cfg.n_bins, HRL_ANT_MAZE: 28 + (cfg.n_bins if cfg.sense_walls else 0),
-            HRL_ANT_FLAGRUN: 28, HRL_ANT_MJ: 29, HRL_ANT_MAZE_MJ: 30 + 3 * cfg.n_bins,
-            HRL_POINT_GATHER: 8 + 2 * cfg.n_bins}[k]
+    return {HRL_ANT_GATHER: 26 + food_obs_dim(cfg),
+            HRL_ANT_MAZE: 26 + (cfg.n_bins if cfg.sense_target else 2) + (cfg.n_bins if cfg.sense_walls else 0),
+            HRL_ANT_FLAGRUN: 28 + (cfg.n_bins if cfg.flag_use_sensor else 0), HRL_ANT_MJ: 29, HRL_ANT_MAZE_MJ: 30 + 3 * cfg.n_bins,
+            HRL_POINT_GATHER: 8 + food_obs_dim(cfg)}[k]
 
 
 def act_dim(cfg):

@@ -96,6 +96,22 @@ __device__ __noinline__ void flag_goal(const hrl_config& cfg, int ep, int j, flo
   }
 }
 
+// create_close_target (ant_flagrun_env.py:80-89, max_targets <= 0): per-axis offset of magnitude
+// U(tol, max_target_dist / 2) with a random sign around the true torso xy, redrawn until strictly inside the world
+__device__ __noinline__ void flag_close_target(const hrl_config& cfg, uint32_t genv, int steps_total, int at_reset, float px,
+                                               float py, float& gx, float& gy) {
+  const float wb = cfg.flag_size * 0.5f, lo = cfg.tol, hi = cfg.flag_max_target_dist * 0.5f;
+  float g0 = wb + 1.f, g1 = wb + 1.f;
+  for (uint32_t attempt = 0; attempt < HRL_MAX_PLACE_ATTEMPTS; attempt++) {
+    float u[4];
+    rng_u4(cfg.flag_seed, genv, STREAM_FLAG_CLOSE, (uint32_t)steps_total, attempt * 2 + (at_reset ? 1u : 0u), u);
+    g0 = (lo + (hi - lo) * u[0]) * (u[2] < 0.5f ? -1.f : 1.f) + px;
+    g1 = (lo + (hi - lo) * u[1]) * (u[3] < 0.5f ? -1.f : 1.f) + py;
+    if (-wb < g0 && g0 < wb && -wb < g1 && g1 < wb) break;
+  }
+  gx = g0; gy = g1;
+}
+
 // gather_scene.py:52-62: uniform on the (size-1)^2 square, rejected while closer than `spacing`
 // to (ax, ay).  Evaluated in double from 24-bit uniforms and rounded to f32 (bit-identical to the oracle).
 __device__ __noinline__ void place_item(const hrl_config& cfg, uint32_t genv, uint32_t stream, uint32_t draw,
@@ -117,6 +133,21 @@ struct TaskRegs {  // replicated per-env task state held in registers
   float feet[4];
   int t, episode, steps_total, goals_left, since, rewarded;
 };
+
+// Flagrun next_target() (ant_flagrun_env.py:112-120): pop the next pre-drawn goal, or draw a close one
+// when max_targets <= 0; the potential restarts from the STALE walk_target_dist (quirk Q3).
+// false = goal list exhausted (the reference's IndexError -> done).
+__device__ __forceinline__ bool flag_next(const hrl_config& cfg, uint32_t genv, TaskRegs& T, float px, float py, int at_reset) {
+  if (cfg.flag_max_targets < 1) flag_close_target(cfg, genv, T.steps_total, at_reset, px, py, T.tx, T.ty);
+  else {
+    if (T.goals_left <= 0) return false;
+    T.goals_left--;
+    flag_goal(cfg, T.episode - 1, T.goals_left, T.tx, T.ty);
+  }
+  T.rewarded = 0;
+  T.potential = -T.wtd / cfg.dt;
+  return true;
+}
 
 // ------------------------------------------------------------------------------------------
 // fused Ant step kernel
@@ -306,30 +337,64 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
         }
       }
       food_rew = gsum(food_rew);
-      // sector sensor (:128-177): nearest item wins per bin
       const int nb = cfg.n_bins;
-      for (int i = lane; i < HRL_EPW * 2 * HRL_MAX_BINS; i += 32) sbins[i] = 0x7ff0000000000000ull;
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int gi = 4 * k + i;
-        if (gi >= cfg.n_food + cfg.n_poison) continue;
-        double d2;
-        const int b = gather_item_bin(s.O.x, s.O.y, yaw, it_x[i], it_y[i], nb, cfg.sensor_range, cfg.sensor_span, &d2);
-        if (b >= 0) atomicMin(&sbins[(es * 2 + (gi < cfg.n_food ? 0 : 1)) * HRL_MAX_BINS + b], (unsigned long long)__double_as_longlong(d2));
-      }
-      __syncwarp();
       if (commit) {
         if (k == 0) {
           so[0] = o_z; so[1] = o_v0; so[2] = o_v1; so[3] = o_v2; so[4] = o_r; so[5] = o_p;
           so[22] = T.feet[0]; so[23] = T.feet[1]; so[24] = T.feet[2]; so[25] = T.feet[3];
         }
         so[6 + 4 * k] = clip5(rel1); so[7 + 4 * k] = clip5(sp1); so[8 + 4 * k] = clip5(rel2); so[9 + 4 * k] = clip5(sp2);
-        for (int b = k; b < 2 * nb; b += 4) {
-          const int ty = b / nb, bb = b - ty * nb;
-          const unsigned long long bits = sbins[(es * 2 + ty) * HRL_MAX_BINS + bb];
-          so[26 + b] = bits == 0x7ff0000000000000ull ? 0.f : (float)(1.0 - __longlong_as_double((long long)bits) / (double)cfg.sensor_range);
+      }
+      if (cfg.use_sensor) {
+        // sector sensor (:128-177): nearest item wins per bin
+        for (int i = lane; i < HRL_EPW * 2 * HRL_MAX_BINS; i += 32) sbins[i] = 0x7ff0000000000000ull;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int gi = 4 * k + i;
+          if (gi >= cfg.n_food + cfg.n_poison) continue;
+          double d2;
+          const int b = gather_item_bin(s.O.x, s.O.y, yaw, it_x[i], it_y[i], nb, cfg.sensor_range, cfg.sensor_span, &d2);
+          if (b >= 0) atomicMin(&sbins[(es * 2 + (gi < cfg.n_food ? 0 : 1)) * HRL_MAX_BINS + b], (unsigned long long)__double_as_longlong(d2));
         }
+        __syncwarp();
+        if (commit) {
+          for (int b = k; b < 2 * nb; b += 4) {
+            const int ty = b / nb, bb = b - ty * nb;
+            const unsigned long long bits = sbins[(es * 2 + ty) * HRL_MAX_BINS + bb];
+            so[26 + b] = bits == 0x7ff0000000000000ull ? 0.f : (float)(1.0 - __longlong_as_double((long long)bits) / (double)cfg.sensor_range);
+          }
+        }
+      } else {
+        // use_sensor=False -> get_abs_pos (:179-196): world xy of the min(n_bins, n) nearest food items, then
+        // poison items, each sorted by squared distance (stable).  Rank = number of same-type items that sort
+        // before this one; the 16 exact float64 distances are exchanged through shared memory.
+        double* sd2 = reinterpret_cast<double*>(sbins + es * 2 * HRL_MAX_BINS);
+        double d2v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const double dx = __dsub_rn((double)it_x[i], (double)s.O.x), dy = __dsub_rn((double)it_y[i], (double)s.O.y);
+          d2v[i] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+          sd2[4 * k + i] = d2v[i];
+        }
+        __syncwarp();
+        if (commit) {
+          const int keep_f = min(nb, cfg.n_food), keep_p = min(nb, cfg.n_poison);
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int gi = 4 * k + i;
+            if (gi >= cfg.n_food + cfg.n_poison) continue;
+            const bool poison = gi >= cfg.n_food;
+            const int first = poison ? cfg.n_food : 0, cnt = poison ? cfg.n_poison : cfg.n_food;
+            int rank = 0;
+            for (int j = first; j < first + cnt; j++) rank += (sd2[j] < d2v[i] || (sd2[j] == d2v[i] && j < gi)) ? 1 : 0;
+            if (rank < (poison ? keep_p : keep_f)) {
+              const int at = 26 + (poison ? 2 * keep_f : 0) + 2 * rank;
+              so[at] = it_x[i]; so[at + 1] = it_y[i];
+            }
+          }
+        }
+        __syncwarp();
       }
       fin = isfinite(o_z) && isfinite(o_v0) && isfinite(o_v1) && isfinite(o_v2) && isfinite(o_r) && isfinite(o_p) &&
             isfinite(rel1) && isfinite(sp1) && isfinite(rel2) && isfinite(sp2);
@@ -377,25 +442,31 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
           so[6 + off + 4 * k] = clip5(rel1); so[7 + off + 4 * k] = clip5(sp1);
           so[8 + off + 4 * k] = clip5(rel2); so[9 + off + 4 * k] = clip5(sp2);
           if (kind == HRL_ANT_MAZE) {
-            if (k == 0) {  // ant_maze_bullet_env.py:123-133 (true torso xy, not the Q1 mean)
+            int nt = 2;
+            if (cfg.sense_target) {  // ant_maze_bullet_env.py:135-178: wtd is the Q1-distorted distance, the pose the true one
+              nt = cfg.n_bins;
+              const int tb = maze_target_bin(cfg.n_bins, cfg.sensor_span, cfg.sensor_range, cfg.has_box ? 3 : 0, bounds + 16, s.O.x,
+                                             s.O.y, yaw, T.tx, T.ty, wtd_new);
+              for (int b = k; b < nt; b += 4) so[26 + b] = (b == tb) ? (float)(1.0 - (double)wtd_new / (double)cfg.sensor_range) : 0.f;
+            } else if (k == 0) {  // ant_maze_bullet_env.py:123-133 (true torso xy, not the Q1 mean)
               const float vx = T.tx - s.O.x, vy = T.ty - s.O.y;
               if (cfg.target_encoding == 0) { const float nn = sqrtf(vx * vx + vy * vy); so[26] = vx / nn; so[27] = vy / nn; }
               else { float sa, ca; sincosf(atan2f(vy, vx) - yaw, &sa, &ca); so[26] = sa; so[27] = ca; }
             }
             if (cfg.sense_walls)
               for (int b = k; b < cfg.n_bins; b += 4)
-                so[28 + b] = lidar_ray(b, cfg.n_bins, cfg.sensor_span, cfg.sensor_range, n_lines, bounds, s.O.x, s.O.y, yaw);
+                so[26 + nt + b] = lidar_ray(b, cfg.n_bins, cfg.sensor_span, cfg.sensor_range, n_lines, bounds, s.O.x, s.O.y, yaw);
           }
+          if (kind == HRL_ANT_FLAGRUN && cfg.flag_use_sensor)  // ant_flagrun_env.py:122-130 (body_real_xyz = torso)
+            for (int b = k; b < cfg.n_bins; b += 4)
+              so[28 + b] = lidar_ray(b, cfg.n_bins, cfg.sensor_span, cfg.sensor_range, n_lines, bounds, s.O.x, s.O.y, yaw);
         }
       }
       if (todo == 2) {
         // Flagrun reset stage 1 (ant_flagrun_env.py:141-153): calc_state with the STALE target,
         // then next_target(): potential from that stale distance (quirk Q3)
         T.wtd = wtd_new;
-        T.goals_left--;
-        flag_goal(cfg, T.episode - 1, T.goals_left, T.tx, T.ty);
-        T.rewarded = 0;
-        T.potential = -T.wtd / cfg.dt;
+        flag_next(cfg, genv, T, s.O.x, s.O.y, 1);
       }
       if (commit) {
         T.wtd = wtd_new;
@@ -423,24 +494,29 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
         for (int j = 0; j < 4; j++) T.feet[j] = (float)__shfl_sync(HRL_FULL_MASK, feet_ground, (lane & ~3) | j);
         float rew = inner, info1 = 0.f;
         int next = 0;
-        if (kind == HRL_ANT_MAZE || kind == HRL_ANT_MAZE_MJ) {
-          rew = inner * cfg.inner_rew_weight;  // ant_maze_bullet_env.py:84, ant_maze_mj_env.py:73
-          if (T.wtd < cfg.tol && (cfg.done_at_target || kind == HRL_ANT_MAZE_MJ)) { rew += 1.f; done = 1; }
+        if (kind == HRL_ANT_MAZE) {
+          // ant_maze_bullet_env.py:84-96; the reference's self.t (incremented at :78) is T.t + 1
+          rew = inner * cfg.inner_rew_weight;
+          const bool last = (T.t + 1 == cfg.maze_max_steps - 1);
+          if (T.wtd < cfg.tol && (cfg.done_at_target || last)) { rew += 1.f; done = 1; }
+          if (last) done = 1;
+          if (cfg.targ_dist_rew && done) rew -= T.wtd;
+        } else if (kind == HRL_ANT_MAZE_MJ) {
+          rew = inner * cfg.inner_rew_weight;  // ant_maze_mj_env.py:73-77
+          if (T.wtd < cfg.tol) { rew += 1.f; done = 1; }
         } else if (kind == HRL_ANT_FLAGRUN) {
           // ant_flagrun_env.py:162-204
           T.since += 1;
           if (T.wtd < cfg.tol) {
             if (!T.rewarded) { rew += cfg.goal_reach_rew; T.rewarded = 1; }
-            if (T.goals_left > 0) {
-              T.goals_left--; flag_goal(cfg, T.episode - 1, T.goals_left, T.tx, T.ty);
-              T.rewarded = 0; T.potential = -T.wtd / cfg.dt; T.since = 0; next = 1;
-            } else done = 1;
+            if (cfg.flag_switch_on_collision) {
+              if (flag_next(cfg, genv, T, s.O.x, s.O.y, 0)) { T.since = 0; next = 1; }
+              else done = 1;
+            }
           }
           if (cfg.flag_timeout > 0 && cfg.flag_timeout <= T.since) {
-            if (T.goals_left > 0) {
-              T.goals_left--; flag_goal(cfg, T.episode - 1, T.goals_left, T.tx, T.ty);
-              T.rewarded = 0; T.potential = -T.wtd / cfg.dt; T.since = 0; next = 1;
-            } else done = 1;
+            if (flag_next(cfg, genv, T, s.O.x, s.O.y, 0)) { T.since = 0; next = 1; }
+            else done = 1;
           }
           info1 = (float)T.goals_left;
         }
@@ -809,6 +885,9 @@ int hrl_default_config(int32_t kind, int32_t num_envs, hrl_config* c) {
   // ant_flagrun_env.py:14-16,157-160
   c->flag_max_targets = 100; c->flag_timeout = 200; c->flag_size = 10.f; c->goal_reach_rew = 5000.f; c->flag_seed = 123;
   c->electricity_cost = -2.0f; c->stall_torque_cost = -0.1f; c->joints_at_limit_cost = -0.1f;
+  // non-default kwargs: off unless asked for
+  c->sense_target = 0; c->maze_max_steps = -1; c->targ_dist_rew = 0;
+  c->flag_use_sensor = 0; c->flag_switch_on_collision = 1; c->flag_max_target_dist = 0.f;
   switch (kind) {
     case HRL_ANT_GATHER:
       c->world_size[0] = c->world_size[1] = 15; c->start_pos[2] = 0.75f; break;
@@ -834,6 +913,7 @@ int hrl_default_config(int32_t kind, int32_t num_envs, hrl_config* c) {
       c->world_size[0] = c->world_size[1] = 12; c->start_pos[2] = 0.25f; c->tol = 0.5f;
       c->n_scene_parts = 2; c->scene_parts_sum[0] = -6; c->scene_parts_sum[1] = 0;
       c->electricity_cost = 0; c->stall_torque_cost = 0; c->joints_at_limit_cost = 0;
+      c->n_bins = 8; c->sensor_span = (float)HRL_PI_D; c->sensor_range = 4.f;  // ant_flagrun_env.py:15 (read when use_sensor)
       break;
     case HRL_ANT_MJ:  // envs/MjAnt.py:31 on the pybulletgym stadium ground
       c->world_size[0] = c->world_size[1] = 50; c->has_walls = 0; c->ground_z = 0.f; c->start_pos[2] = 0.75f; break;
@@ -842,12 +922,17 @@ int hrl_default_config(int32_t kind, int32_t num_envs, hrl_config* c) {
   return HRL_OK;
 }
 
+static int food_obs_dim(const hrl_config* c) {  // 2 n_bins sector readings, or the xy of the nearest items (use_sensor=False)
+  if (c->use_sensor) return 2 * c->n_bins;
+  const int kf = c->n_bins < c->n_food ? c->n_bins : c->n_food, kp = c->n_bins < c->n_poison ? c->n_bins : c->n_poison;
+  return 2 * kf + 2 * kp;
+}
 int hrl_obs_dim(const hrl_config* c) {
   if (!c) return -1;
   switch (c->env_kind) {
-    case HRL_ANT_GATHER: return 26 + 2 * c->n_bins;                     // ant_gather_env.py:54-55
-    case HRL_ANT_MAZE: return 26 + 2 + (c->sense_walls ? c->n_bins : 0);  // ant_maze_bullet_env.py:54-57
-    case HRL_ANT_FLAGRUN: return 28;
+    case HRL_ANT_GATHER: return 26 + food_obs_dim(c);                    // ant_gather_env.py:54-55,179-196
+    case HRL_ANT_MAZE: return 26 + (c->sense_target ? c->n_bins : 2) + (c->sense_walls ? c->n_bins : 0);  // ant_maze_bullet_env.py:54-57
+    case HRL_ANT_FLAGRUN: return 28 + (c->flag_use_sensor ? c->n_bins : 0);  // ant_flagrun_env.py:52-54
     case HRL_ANT_MJ: return 29;                                          // MjAnt.py:15
     case HRL_ANT_MAZE_MJ: return 29 + 3 * c->n_bins + 1;                 // ant_maze_mj_env.py:50
     case HRL_POINT_GATHER: return 8 + 2 * c->n_bins;                     // gather_base.py:54-55
@@ -878,6 +963,10 @@ static int validate(const hrl_config* c) {
   if (c->n_food < 0 || c->n_food > 8 || c->n_poison < 0 || c->n_poison > 8) return set_err(HRL_E_INVALID, "n_food/n_poison out of range");
   if (c->substeps < 1 || c->solver_iters < 0) return set_err(HRL_E_INVALID, "bad substeps/solver_iters");
   if (c->n_targets > HRL_MAX_TARGETS || c->flag_max_targets > 127) return set_err(HRL_E_INVALID, "too many targets");
+  if (c->env_kind == HRL_POINT_GATHER && !c->use_sensor) return set_err(HRL_E_INVALID, "PointGather use_sensor=False is not built");
+  if (c->env_kind == HRL_ANT_FLAGRUN && c->flag_max_targets < 1 && !(c->flag_max_target_dist > 0.f))
+    return set_err(HRL_E_INVALID, "flagrun needs max_targets > 0 or max_target_dist > 0 (ant_flagrun_env.py:17-18)");
+  if (c->env_kind == HRL_ANT_FLAGRUN && c->flag_use_sensor && c->n_bins < 2) return set_err(HRL_E_INVALID, "flagrun sensor needs >= 2 bins");
   if ((c->env_kind == HRL_ANT_MAZE || c->env_kind == HRL_ANT_MAZE_MJ) && c->n_targets < 1) return set_err(HRL_E_INVALID, "maze needs targets");
   return HRL_OK;
 }

@@ -103,6 +103,46 @@ __device__ __forceinline__ float lidar_ray(int i, int n_bins, float span_f, floa
   return (float)best;
 }
 
+// intersection_utils.py:14-71 (orientation test + collinear cases), float64 like the reference
+__device__ __forceinline__ int orient_d(double px, double py, double qx, double qy, double rx, double ry) {
+  const double val = __dsub_rn(__dmul_rn(__dsub_rn(qy, py), __dsub_rn(rx, qx)), __dmul_rn(__dsub_rn(qx, px), __dsub_rn(ry, qy)));
+  return val > 0 ? 1 : (val < 0 ? 2 : 0);
+}
+__device__ __forceinline__ bool on_seg_d(double px, double py, double qx, double qy, double rx, double ry) {
+  return qx <= fmax(px, rx) && qx >= fmin(px, rx) && qy <= fmax(py, ry) && qy >= fmin(py, ry);
+}
+__device__ __forceinline__ bool segment_intersection_d(double p1x, double p1y, double q1x, double q1y, double p2x, double p2y,
+                                                       double q2x, double q2y) {
+  const int o1 = orient_d(p1x, p1y, q1x, q1y, p2x, p2y), o2 = orient_d(p1x, p1y, q1x, q1y, q2x, q2y);
+  const int o3 = orient_d(p2x, p2y, q2x, q2y, p1x, p1y), o4 = orient_d(p2x, p2y, q2x, q2y, q1x, q1y);
+  if (o1 != o2 && o3 != o4) return true;
+  if (o1 == 0 && on_seg_d(p1x, p1y, p2x, p2y, q1x, q1y)) return true;
+  if (o2 == 0 && on_seg_d(p1x, p1y, q2x, q2y, q1x, q1y)) return true;
+  if (o3 == 0 && on_seg_d(p2x, p2y, p1x, p1y, q2x, q2y)) return true;
+  if (o4 == 0 && on_seg_d(p2x, p2y, q1x, q1y, q2x, q2y)) return true;
+  return false;
+}
+
+// Maze goal sector sensor, ant_maze_bullet_env.py:135-178 (sense_target=True): one reading
+// 1 - walk_target_dist / range in the bin of the goal direction, nothing when the goal is out of
+// range, outside the span, or hidden behind one of the 3 box_bounds segments (maze_scene.py:19-21).
+// Evaluated in float64 with the reference's expression sequence (rare, non-default path).
+__device__ __noinline__ int maze_target_bin(int n_bins, float span_f, float range_f, int n_box, const float* __restrict__ box,
+                                            float rx, float ry, float yaw, float tx, float ty, float wtd) {
+  if (n_bins <= 0 || (double)wtd > (double)range_f) return -1;
+  for (int l = 0; l < n_box; l++)
+    if (segment_intersection_d(rx, ry, tx, ty, box[4 * l], box[4 * l + 1], box[4 * l + 2], box[4 * l + 3])) return -1;
+  double ad = atan2(__dsub_rn((double)ty, (double)ry), __dsub_rn((double)tx, (double)rx)) - (double)yaw;
+  ad = fmod(ad, 2.0 * HRL_PI_D);
+  if (ad < 0.0) ad += 2.0 * HRL_PI_D;
+  if (ad > HRL_PI_D) ad -= 2.0 * HRL_PI_D;
+  if (ad < -HRL_PI_D) ad += 2.0 * HRL_PI_D;
+  const double spand = snap_span(span_f), halfd = spand * 0.5, resd = spand / (double)n_bins;
+  if (fabs(ad) > halfd) return -1;
+  const int b = (int)((ad + halfd) / resd);
+  return b > n_bins - 1 ? n_bins - 1 : b;
+}
+
 // Bullet getEulerFromQuaternion (SURVEY.md A.3 "Queries").  Also returns cos/sin of the yaw: outside
 // the gimbal branch they follow from the atan2 arguments with one rsqrt (no sincos evaluation).
 __device__ __forceinline__ void quat_to_rpy(float x, float y, float z, float w, float& roll, float& pitch, float& yaw,

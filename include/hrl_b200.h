@@ -122,6 +122,13 @@ typedef struct hrl_config {
   uint64_t flag_seed;       /* 123: goal stream shared by all envs (ant_flagrun_env.py:39) */
   /* reward weights of the third-party walker step */
   float electricity_cost, stall_torque_cost, joints_at_limit_cost;
+  /* non-default ctor kwargs; appended so that the layout above is stable */
+  int32_t sense_target;      /* ant_maze_bullet_env.py:24,135-178: goal sector sensor replaces the 2-d goal vector */
+  int32_t maze_max_steps;    /* ant_maze_bullet_env.py:25,86-91: max_steps, -1 = off                        */
+  int32_t targ_dist_rew;     /* ant_maze_bullet_env.py:25,93-94                                               */
+  int32_t flag_use_sensor;   /* ant_flagrun_env.py:15,122-130: wall lidar appended (n_bins, sensor_span, sensor_range) */
+  int32_t flag_switch_on_collision; /* ant_flagrun_env.py:16,187-194, default 1                               */
+  float flag_max_target_dist;/* ant_flagrun_env.py:14,80-89: create_close_target when flag_max_targets <= 0   */
 } hrl_config;
 
 typedef struct hrl_handle hrl_handle;

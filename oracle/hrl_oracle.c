@@ -75,7 +75,7 @@ static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
  *   item reset       : stream ITEM_RESET, draw = episode,            sub = item*64 + attempt
  *   maze goal        : stream GOAL,       draw = episode,            sub = 0
  *   flagrun goal j   : stream FLAG (key flag_seed, env 0), draw = attempt, sub = episode*128 + j */
-enum { STREAM_JOINT = 0, STREAM_ITEM = 1, STREAM_GOAL = 2, STREAM_FLAG = 3, STREAM_ITEM_RESET = 4 };
+enum { STREAM_JOINT = 0, STREAM_ITEM = 1, STREAM_GOAL = 2, STREAM_FLAG = 3, STREAM_ITEM_RESET = 4, STREAM_FLAG_CLOSE = 5 };
 #define MAX_PLACE_ATTEMPTS 16
 /* 4 uniforms in [0,1) with 24 bits each (exact in float and double) */
 static void rng_u4(uint64_t seed, uint32_t env, uint32_t stream, uint32_t draw, uint32_t sub, real u[4]) {
@@ -279,6 +279,9 @@ struct hrlo_env {
   env_state* s;
   /* instrumentation: flop-model inputs */
   double n_contacts, n_limit_rows, n_substeps;
+  /* golden-vector replay (tests only): goal list instead of the Philox stream, stub robot */
+  const double* replay_goals; /* [flag_max_targets][2], popped from the end like the reference */
+  int replay_stub_robot;      /* next_target(): calc_potential() = -1, calc_state() leaves wtd alone */
 };
 typedef struct hrlo_env hrlo_env;
 
@@ -859,6 +862,30 @@ void hrlo_sense_walls_one(int n_bins, double span, double range, int n_lines, co
   }
 }
 
+/* Maze goal sector sensor - ant_maze_bullet_env.py:135-178, in double like the reference.
+ * `wtd` is the (Q1-distorted) robot.walk_target_dist, the pose is the true torso pose; the goal is
+ * hidden when the segment robot->goal crosses one of the box_bounds segments (maze_scene.py:19-21). */
+void hrlo_maze_target_sensor(int n_bins, double span, double range, int n_box, const double* box_bounds, double rx,
+                             double ry, double yaw, double tx, double ty, double wtd, double* readings) {
+  for (int b = 0; b < n_bins; b++) readings[b] = 0;
+  if (n_bins <= 0) return;
+  if (wtd > range) return; /* :145 */
+  for (int l = 0; l < n_box; l++) {
+    const double sgm[8] = {rx, ry, tx, ty, box_bounds[4 * l], box_bounds[4 * l + 1], box_bounds[4 * l + 2], box_bounds[4 * l + 3]};
+    if (hrlo_segment_intersection(sgm)) return; /* :148-150 */
+  }
+  double ang = atan2(ty - ry, tx - rx) - yaw; /* :153 */
+  ang = fmod(ang, 2 * PI_D);
+  if (ang < 0) ang += 2 * PI_D; /* Python % */
+  if (ang > PI_D) ang -= 2 * PI_D;
+  if (ang < -PI_D) ang += 2 * PI_D;
+  double half = span * 0.5, res = span / n_bins;
+  if (fabs(ang) > half) return; /* :164 */
+  int bin = (int)((ang + half) / res);
+  if (bin > n_bins - 1) bin = n_bins - 1; /* the reference raises IndexError at exactly +half span */
+  readings[bin] = 1.0 - wtd / range; /* :167 */
+}
+
 /* gather_scene.py:52-62; returns number of (x,y) attempts consumed.  Attempt k of this
  * placement is Philox(draw, env, stream, item*64+k); replay != NULL replays uniforms instead. */
 static int random_on_plane(const hrl_config* cfg, real ax, real ay, uint64_t seed, uint32_t env, uint32_t stream,
@@ -945,6 +972,43 @@ static void items_to_double(const env_state* s, double* it) {
   for (int i = 0; i < HRL_MAX_ITEMS; i++) { it[2 * i] = (double)s->items[i][0]; it[2 * i + 1] = (double)s->items[i][1]; }
 }
 
+static int imin(int a, int b) { return a < b ? a : b; }
+/* width of the food/poison part of a Gather observation: 2 n_bins sector readings, or with
+ * use_sensor=False the xy of the min(n_bins, n) nearest food and poison items
+ * (ant_gather_env.py:179-196; the reference's observation_space keeps the sensor width, :54-55) */
+static int food_obs_dim(const hrl_config* c) {
+  if (c->use_sensor) return 2 * c->n_bins;
+  return 2 * imin(c->n_bins, c->n_food) + 2 * imin(c->n_bins, c->n_poison);
+}
+/* get_food_obs (ant_gather_env.py:120-124): sector sensor or get_abs_pos (:179-196, twin
+ * gather_base.py:170-187): items of each type sorted by squared distance (stable), first n_bins, world xy */
+static void food_obs(const hrl_config* cfg, const env_state* s, real yaw, real* out) {
+  if (cfg->use_sensor) {
+    double it[2 * HRL_MAX_ITEMS], fo[HRL_MAX_BINS], po[HRL_MAX_BINS];
+    items_to_double(s, it);
+    /* items are stored food-first; with n_food < 8 the poison block still starts at index n_food */
+    hrlo_gather_sensor_one(cfg->n_bins, cfg->sensor_range, snap_span(cfg->sensor_span), (double)s->pos[0], (double)s->pos[1],
+                           (double)yaw, it, cfg->n_food, cfg->n_poison, NULL, fo, po, NULL);
+    for (int b = 0; b < cfg->n_bins; b++) { out[b] = (real)fo[b]; out[cfg->n_bins + b] = (real)po[b]; }
+    return;
+  }
+  int o = 0;
+  for (int ty = 0; ty < 2; ty++) {
+    int first = ty ? cfg->n_food : 0, n = ty ? cfg->n_poison : cfg->n_food, keep = imin(cfg->n_bins, n);
+    double d2[8]; int idx[8];
+    for (int i = 0; i < n; i++) {
+      double dx = (double)s->items[first + i][0] - (double)s->pos[0], dy = (double)s->items[first + i][1] - (double)s->pos[1];
+      d2[i] = dx * dx + dy * dy; idx[i] = i;
+    }
+    for (int i = 1; i < n; i++) { /* stable insertion sort = Python sorted() */
+      int k = idx[i], j = i - 1;
+      while (j >= 0 && d2[idx[j]] > d2[k]) { idx[j + 1] = idx[j]; j--; }
+      idx[j + 1] = k;
+    }
+    for (int i = 0; i < keep; i++) { out[o++] = s->items[first + idx[i]][0]; out[o++] = s->items[first + idx[i]][1]; }
+  }
+}
+
 /* Gather task layer after physics: ant_gather_env.py:84-119 / gather_base.py:80-109.
  * `base` = robot obs (ant: 26 = state[0], state[3:]; point: 8).  replay != NULL replays uniforms. */
 static void gather_task(hrlo_env* E, int e, env_state* s, const real* base, int nbase, real z_for_alive, int can_die,
@@ -970,16 +1034,11 @@ static void gather_task(hrlo_env* E, int e, env_state* s, const real* base, int 
     }
   }
   if (replay_used) *replay_used = used;
-  double it[2 * HRL_MAX_ITEMS], fo[HRL_MAX_BINS], po[HRL_MAX_BINS];
-  items_to_double(s, it);
-  /* items are stored food-first; with n_food < 8 the poison block still starts at index n_food */
-  hrlo_gather_sensor_one(cfg->n_bins, cfg->sensor_range, snap_span(cfg->sensor_span), (double)s->pos[0], (double)s->pos[1],
-                         (double)yaw, it, cfg->n_food, cfg->n_poison, NULL, fo, po, NULL);
   for (int i = 0; i < nbase; i++) obs[i] = base[i];
-  for (int b = 0; b < cfg->n_bins; b++) { obs[nbase + b] = (real)fo[b]; obs[nbase + cfg->n_bins + b] = (real)po[b]; }
+  food_obs(cfg, s, yaw, obs + nbase);
   int alive = can_die ? (z_for_alive > (real)0.26) : 1; /* Ant.alive_bonus; point_bot.py:73-74 */
   *done = !alive;
-  if (!all_finite(obs, nbase + 2 * cfg->n_bins)) *done = 1; /* :101-103 */
+  if (!all_finite(obs, nbase + food_obs_dim(cfg))) *done = 1; /* :101-103 */
   real dead_rew = alive ? 0 : (real)cfg->dying_cost;
   *rew = food_rew + dead_rew;
   info[0] = food_rew; info[1] = dead_rew;
@@ -1022,6 +1081,8 @@ static void joint_noise(hrlo_env* E, int e, env_state* s) {
 static int is_ant(int kind) { return kind != HRL_POINT_GATHER; }
 
 int hrlo_scene_bounds(const hrl_config* cfg, double* b);
+void hrlo_maze_target_sensor(int n_bins, double span, double range, int n_box, const double* box_bounds, double rx,
+                             double ry, double yaw, double tx, double ty, double wtd, double* readings);
 
 static void lidar(const hrl_config* cfg, const env_state* s, real yaw, real* out) {
   double bounds[7 * 4], w[HRL_MAX_BINS];
@@ -1031,11 +1092,18 @@ static void lidar(const hrl_config* cfg, const env_state* s, real yaw, real* out
   for (int b = 0; b < cfg->n_bins; b++) out[b] = (real)w[b];
 }
 
+/* PointBot.calc_state (point_bot.py:48-67) for a general pose; walk target (0,0), initial_z 1 */
+static void point_state_general(const real xyz[3], const real rpy[3], const real vel[3], real initial_z, real* o) {
+  real a = R_ATAN2(0 - xyz[1], 0 - xyz[0]) - rpy[2];
+  real cy = R_COS(-rpy[2]), sy = R_SIN(-rpy[2]);
+  o[0] = xyz[2] - initial_z; o[1] = R_SIN(a); o[2] = R_COS(a);
+  o[3] = (real)0.3 * (cy * vel[0] - sy * vel[1]); o[4] = (real)0.3 * (sy * vel[0] + cy * vel[1]); o[5] = (real)0.3 * vel[2];
+  o[6] = rpy[0]; o[7] = rpy[1];
+}
 static void point_base_obs(const env_state* s, real* o) {
-  /* point_bot.py:48-67 with roll = pitch = yaw = 0 (translation-only body), walk target (0,0) */
-  real a = R_ATAN2(0 - s->pos[1], 0 - s->pos[0]);
-  o[0] = s->pos[2] - s->initial_z; o[1] = R_SIN(a); o[2] = R_COS(a);
-  o[3] = (real)0.3 * s->vel[0]; o[4] = (real)0.3 * s->vel[1]; o[5] = (real)0.3 * s->vel[2]; o[6] = 0; o[7] = 0;
+  /* the cube of this build only translates: roll = pitch = yaw = 0 */
+  const real rpy[3] = {0, 0, 0};
+  point_state_general(s->pos, rpy, s->vel, s->initial_z, o);
 }
 
 /* Observation assembled from a calc_state result `c` (ants) and the task state.  Used for
@@ -1044,24 +1112,32 @@ static void compose_obs(const hrlo_env* E, const env_state* s, const calc_t* c, 
   const hrl_config* cfg = &E->cfg;
   switch (cfg->env_kind) {
     case HRL_ANT_GATHER: { /* ant_gather_env.py:68-74 */
-      double it[2 * HRL_MAX_ITEMS], fo[HRL_MAX_BINS], po[HRL_MAX_BINS];
-      items_to_double(s, it);
-      hrlo_gather_sensor_one(cfg->n_bins, cfg->sensor_range, snap_span(cfg->sensor_span), (double)s->pos[0], (double)s->pos[1],
-                             (double)c->rpy[2], it, cfg->n_food, cfg->n_poison, NULL, fo, po, NULL);
       obs[0] = c->obs28[0];
       for (int i = 3; i < 28; i++) obs[i - 2] = c->obs28[i];
-      for (int b = 0; b < cfg->n_bins; b++) { obs[26 + b] = (real)fo[b]; obs[26 + cfg->n_bins + b] = (real)po[b]; }
+      food_obs(cfg, s, c->rpy[2], obs + 26);
     } break;
     case HRL_ANT_MAZE: { /* ant_maze_bullet_env.py:63-75, :123-133 */
       obs[0] = c->obs28[0];
       for (int i = 3; i < 28; i++) obs[i - 2] = c->obs28[i];
-      real vx = s->target[0] - s->pos[0], vy = s->target[1] - s->pos[1];
-      if (cfg->target_encoding == 0) { real nn = R_SQRT(vx * vx + vy * vy); obs[26] = vx / nn; obs[27] = vy / nn; }
-      else { real a = R_ATAN2(vy, vx) - c->rpy[2]; obs[26] = R_SIN(a); obs[27] = R_COS(a); }
-      if (cfg->sense_walls) lidar(cfg, s, c->rpy[2], obs + 28);
+      int nt = 2;
+      if (cfg->sense_target) { /* get_target_sensor_obs :135-178 */
+        double rd[HRL_MAX_BINS], bb[7 * 4];
+        hrlo_scene_bounds(cfg, bb);
+        hrlo_maze_target_sensor(cfg->n_bins, snap_span(cfg->sensor_span), (double)cfg->sensor_range, cfg->has_box ? 3 : 0, bb + 16,
+                                (double)s->pos[0], (double)s->pos[1], (double)c->rpy[2], (double)s->target[0],
+                                (double)s->target[1], (double)c->wtd, rd);
+        nt = cfg->n_bins;
+        for (int b = 0; b < nt; b++) obs[26 + b] = (real)rd[b];
+      } else {
+        real vx = s->target[0] - s->pos[0], vy = s->target[1] - s->pos[1];
+        if (cfg->target_encoding == 0) { real nn = R_SQRT(vx * vx + vy * vy); obs[26] = vx / nn; obs[27] = vy / nn; }
+        else { real a = R_ATAN2(vy, vx) - c->rpy[2]; obs[26] = R_SIN(a); obs[27] = R_COS(a); }
+      }
+      if (cfg->sense_walls) lidar(cfg, s, c->rpy[2], obs + 26 + nt);
     } break;
     case HRL_ANT_FLAGRUN:
       for (int i = 0; i < 28; i++) obs[i] = c->obs28[i];
+      if (cfg->flag_use_sensor) lidar(cfg, s, c->rpy[2], obs + 28); /* ant_flagrun_env.py:122-130 (body_real_xyz = torso) */
       break;
     case HRL_ANT_MJ:
     case HRL_ANT_MAZE_MJ: { /* MjAnt.calc_state envs/MjAnt.py:17-25 */
@@ -1078,11 +1154,7 @@ static void compose_obs(const hrlo_env* E, const env_state* s, const calc_t* c, 
     } break;
     case HRL_POINT_GATHER: { /* gather_base.py:67-72 */
       point_base_obs(s, obs);
-      double it[2 * HRL_MAX_ITEMS], fo[HRL_MAX_BINS], po[HRL_MAX_BINS];
-      items_to_double(s, it);
-      hrlo_gather_sensor_one(cfg->n_bins, cfg->sensor_range, snap_span(cfg->sensor_span), (double)s->pos[0], (double)s->pos[1], 0.0,
-                             it, cfg->n_food, cfg->n_poison, NULL, fo, po, NULL);
-      for (int b = 0; b < cfg->n_bins; b++) { obs[8 + b] = (real)fo[b]; obs[8 + cfg->n_bins + b] = (real)po[b]; }
+      food_obs(cfg, s, 0, obs + 8);
     } break;
   }
 }
@@ -1095,16 +1167,67 @@ static void write_obs(const hrlo_env* E, const env_state* s, real* obs) {
 
 /* Flagrun next_target (ant_flagrun_env.py:112-120): pops the next goal; the potential is
  * taken from the STALE cached walk_target_dist (quirk Q3), then calc_state refreshes it. */
-static int flag_next_target(hrlo_env* E, env_state* s, int ep, calc_t* c) {
+static int flag_next_target(hrlo_env* E, int e, env_state* s, int ep, calc_t* c, int at_reset) {
   const hrl_config* cfg = &E->cfg;
-  if (s->goals_left <= 0) return 0; /* goals.pop() raises IndexError */
-  s->goals_left--;
-  flag_goal(cfg, ep, s->goals_left, s->target);
+  if (cfg->flag_max_targets < 1) {
+    /* create_close_target (ant_flagrun_env.py:80-89): offset of magnitude U(tol, max_target_dist/2) per
+     * axis with a random sign around the true torso xy, redrawn until strictly inside the world */
+    real wb = (real)cfg->flag_size / 2, g0 = wb + 1, g1 = wb + 1;
+    for (uint32_t attempt = 0; attempt < MAX_PLACE_ATTEMPTS; attempt++) {
+      real u[4];
+      rng_u4(cfg->flag_seed, (uint32_t)(cfg->env_index_offset + e), STREAM_FLAG_CLOSE, (uint32_t)s->steps_total,
+             attempt * 2 + (uint32_t)(at_reset != 0), u);
+      real lo = (real)cfg->tol, hi = (real)cfg->flag_max_target_dist / 2;
+      g0 = (lo + (hi - lo) * u[0]) * (u[2] < (real)0.5 ? -1 : 1) + s->pos[0];
+      g1 = (lo + (hi - lo) * u[1]) * (u[3] < (real)0.5 ? -1 : 1) + s->pos[1];
+      if (-wb < g0 && g0 < wb && -wb < g1 && g1 < wb) break;
+    }
+    s->target[0] = g0; s->target[1] = g1;
+  } else {
+    if (s->goals_left <= 0) return 0; /* goals.pop() raises IndexError */
+    s->goals_left--;
+    if (E->replay_goals) { s->target[0] = (real)E->replay_goals[2 * s->goals_left]; s->target[1] = (real)E->replay_goals[2 * s->goals_left + 1]; }
+    else flag_goal(cfg, ep, s->goals_left, s->target);
+  }
   s->rewarded = 0;
+  if (E->replay_stub_robot) { s->potential = -1; return 1; }
   s->potential = -s->wtd / (real)cfg->dt;
   ant_calc_state(E, s, c);
   s->wtd = c->wtd;
   return 1;
+}
+
+/* AntMazeBulletEnv.step after the inner walker step (ant_maze_bullet_env.py:84-96); s->t = steps taken
+ * BEFORE this one, the reference's self.t (incremented at :78) is s->t + 1. */
+static int maze_task(const hrl_config* cfg, const env_state* s, real inner, int done, real* rew) {
+  *rew = inner * (real)cfg->inner_rew_weight;
+  const int t = s->t + 1, last = (t == cfg->maze_max_steps - 1);
+  if (s->wtd < (real)cfg->tol) {
+    if (cfg->done_at_target || last) { *rew += 1; done = 1; }
+  }
+  if (last) done = 1;
+  if (cfg->targ_dist_rew && done) *rew -= s->wtd; /* :93-94 */
+  return done;
+}
+
+/* AntFlagrunBulletEnv.step after the inner walker step (ant_flagrun_env.py:167-202). */
+static int flagrun_task(hrlo_env* E, int e, env_state* s, calc_t* c, real inner, int done, real* rew) {
+  const hrl_config* cfg = &E->cfg;
+  real r = inner;
+  s->since += 1;
+  if (s->wtd < (real)cfg->tol) {
+    if (!s->rewarded) { r += (real)cfg->goal_reach_rew; s->rewarded = 1; }
+    if (cfg->flag_switch_on_collision) {
+      if (flag_next_target(E, e, s, s->episode - 1, c, 0)) s->since = 0;
+      else done = 1; /* IndexError -> d = True (:193) */
+    }
+  }
+  if (cfg->flag_timeout > 0 && cfg->flag_timeout <= s->since) {
+    if (flag_next_target(E, e, s, s->episode - 1, c, 0)) s->since = 0;
+    else done = 1;
+  }
+  *rew = r;
+  return done;
 }
 
 static void reset_env(hrlo_env* E, int e, real* obs) {
@@ -1140,7 +1263,7 @@ static void reset_env(hrlo_env* E, int e, real* obs) {
     s->wtd = c.wtd;
     s->goals_left = cfg->flag_max_targets;
     s->rewarded = 0;
-    flag_next_target(E, s, s->episode, &c);
+    flag_next_target(E, e, s, s->episode, &c, 1);
   } else if (is_ant(kind)) {
     ant_calc_state(E, s, &c);
     s->wtd = c.wtd;
@@ -1218,25 +1341,16 @@ static int step_env(hrlo_env* E, int e, const float* act, real* obs, real* rew, 
         if (!all_finite(mj ? obs : c.obs28, mj ? 29 : 28)) done = 1;
       } else if (!all_finite(c.obs28, 28)) done = 1;
       for (int k = 0; k < 4; k++) s->feet[k] = (real)feet_ground[k];
-      if (kind == HRL_ANT_MAZE || kind == HRL_ANT_MAZE_MJ) {
-        /* ant_maze_bullet_env.py:84-89 ; ant_maze_mj_env.py:73-77 */
+      if (kind == HRL_ANT_MAZE) {
+        done = maze_task(cfg, s, inner, done, rew);
+      } else if (kind == HRL_ANT_MAZE_MJ) {
+        /* ant_maze_mj_env.py:73-77 */
         *rew = inner * (real)cfg->inner_rew_weight;
-        if (s->wtd < (real)cfg->tol && (cfg->done_at_target || kind == HRL_ANT_MAZE_MJ)) { *rew += 1; done = 1; }
+        if (s->wtd < (real)cfg->tol) { *rew += 1; done = 1; }
       } else if (kind == HRL_ANT_FLAGRUN) {
         /* ant_flagrun_env.py:162-204 */
-        real r = inner;
-        s->since += 1;
-        if (s->wtd < (real)cfg->tol) {
-          if (!s->rewarded) { r += (real)cfg->goal_reach_rew; s->rewarded = 1; }
-          if (flag_next_target(E, s, s->episode - 1, &c)) s->since = 0;
-          else done = 1; /* IndexError -> d = True (:193) */
-        }
-        if (cfg->flag_timeout > 0 && cfg->flag_timeout <= s->since) {
-          if (flag_next_target(E, s, s->episode - 1, &c)) s->since = 0;
-          else done = 1;
-        }
-        for (int i = 0; i < 28; i++) obs[i] = c.obs28[i];
-        *rew = r;
+        done = flagrun_task(E, e, s, &c, inner, done, rew);
+        compose_obs(E, s, &c, obs); /* the state after a goal switch (:120,190) + optional lidar */
         info[1] = (real)s->goals_left;
       } else {
         *rew = inner;
@@ -1269,6 +1383,8 @@ int hrlo_default_config(int32_t kind, int32_t num_envs, hrl_config* c) {
   c->tol = 1.5f; c->done_at_target = 1; c->inner_rew_weight = 0.f; c->target_encoding = 0; c->sense_walls = 1;
   c->flag_max_targets = 100; c->flag_timeout = 200; c->flag_size = 10.f; c->goal_reach_rew = 5000.f; c->flag_seed = 123;
   c->electricity_cost = -2.0f; c->stall_torque_cost = -0.1f; c->joints_at_limit_cost = -0.1f;
+  c->sense_target = 0; c->maze_max_steps = -1; c->targ_dist_rew = 0;
+  c->flag_use_sensor = 0; c->flag_switch_on_collision = 1; c->flag_max_target_dist = 0.f;
   switch (kind) {
     case HRL_ANT_GATHER:
       c->world_size[0] = c->world_size[1] = 15; c->start_pos[2] = 0.75f; break;
@@ -1295,6 +1411,7 @@ int hrlo_default_config(int32_t kind, int32_t num_envs, hrl_config* c) {
       c->world_size[0] = c->world_size[1] = 12; c->start_pos[2] = 0.25f; c->tol = 0.5f;
       c->n_scene_parts = 2; c->scene_parts_sum[0] = -6; c->scene_parts_sum[1] = 0;
       c->electricity_cost = 0; c->stall_torque_cost = 0; c->joints_at_limit_cost = 0; /* ant_flagrun_env.py:133-135 */
+      c->n_bins = 8; c->sensor_span = (float)PI_D; c->sensor_range = 4.f;            /* :15 (read when use_sensor) */
       break;
     case HRL_ANT_MJ:
       c->world_size[0] = c->world_size[1] = 50; c->has_walls = 0; c->ground_z = 0.f; c->start_pos[2] = 0.75f; break;
@@ -1305,12 +1422,12 @@ int hrlo_default_config(int32_t kind, int32_t num_envs, hrl_config* c) {
 
 int hrlo_obs_dim(const hrl_config* c) {
   switch (c->env_kind) {
-    case HRL_ANT_GATHER: return 26 + 2 * c->n_bins;
-    case HRL_ANT_MAZE: return 26 + 2 + (c->sense_walls ? c->n_bins : 0);
-    case HRL_ANT_FLAGRUN: return 28;
+    case HRL_ANT_GATHER: return 26 + food_obs_dim(c);
+    case HRL_ANT_MAZE: return 26 + (c->sense_target ? c->n_bins : 2) + (c->sense_walls ? c->n_bins : 0);
+    case HRL_ANT_FLAGRUN: return 28 + (c->flag_use_sensor ? c->n_bins : 0);
     case HRL_ANT_MJ: return 29;
     case HRL_ANT_MAZE_MJ: return 29 + 3 * c->n_bins + 1;
-    case HRL_POINT_GATHER: return 8 + 2 * c->n_bins;
+    case HRL_POINT_GATHER: return 8 + food_obs_dim(c);
   }
   return -1;
 }
@@ -1428,11 +1545,76 @@ int hrlo_gather_task_replay(const hrl_config* cfg, const double* base, int nbase
   real b[32], o[64], rew, info[4]; int done;
   for (int i = 0; i < nbase; i++) b[i] = (real)base[i];
   gather_task(E, 0, s, b, nbase, (real)xyz[2], can_die, (real)yaw, uniforms, used, o, &rew, &done, info);
-  for (int i = 0; i < nbase + 2 * c.n_bins; i++) obs[i] = o[i];
+  for (int i = 0; i < nbase + food_obs_dim(&c); i++) obs[i] = o[i];
   for (int i = 0; i < HRL_MAX_ITEMS; i++) { items_xy[2 * i] = s->items[i][0]; items_xy[2 * i + 1] = s->items[i][1]; }
   rew_done_info[0] = rew; rew_done_info[1] = done; rew_done_info[2] = info[0]; rew_done_info[3] = info[1];
   hrlo_destroy(E);
   return HRL_OK;
+}
+
+/* Maze task layer with an injected inner walker step (tests/golden/maze_step.npz):
+ * obs28 = the walker's 28-d state, xy/yaw = true torso pose, wtd = robot.walk_target_dist */
+int hrlo_maze_task_replay(const hrl_config* cfg, const double* obs28, const double xy[2], double yaw, double inner_rew,
+                          int inner_done, double wtd, const double target[2], int t_before, double* obs, double* rew_done) {
+  hrlo_env* E;
+  hrl_config c = *cfg; c.num_envs = 1;
+  if (hrlo_create(&c, &E)) return HRL_E_INVALID;
+  env_state* s = &E->s[0];
+  calc_t cs; memset(&cs, 0, sizeof cs);
+  for (int i = 0; i < 28; i++) cs.obs28[i] = (real)obs28[i];
+  cs.rpy[2] = (real)yaw; cs.wtd = (real)wtd;
+  s->pos[0] = (real)xy[0]; s->pos[1] = (real)xy[1]; s->target[0] = (real)target[0]; s->target[1] = (real)target[1];
+  s->wtd = (real)wtd; s->t = t_before;
+  real o[64], rew;
+  compose_obs(E, s, &cs, o);
+  int done = maze_task(&c, s, (real)inner_rew, inner_done, &rew);
+  for (int i = 0; i < hrlo_obs_dim(&c); i++) obs[i] = o[i];
+  rew_done[0] = rew; rew_done[1] = done;
+  hrlo_destroy(E);
+  return HRL_OK;
+}
+
+/* Flagrun step sequence with a scripted walk_target_dist / inner reward and an injected goal list
+ * (tests/golden/flagrun_step.npz).  Returns the number of steps executed (stops after done). */
+int hrlo_flagrun_replay(const hrl_config* cfg, const double* goals, int n_steps, const double* wtd, const double* inner_r,
+                        double* rew, int* done_out, double* target, int* since, int* rewarded) {
+  hrlo_env* E;
+  hrl_config c = *cfg; c.num_envs = 1;
+  if (hrlo_create(&c, &E)) return HRL_E_INVALID;
+  env_state* s = &E->s[0];
+  E->replay_goals = goals; E->replay_stub_robot = 1;
+  s->episode = 1; s->goals_left = c.flag_max_targets; s->since = 0; s->rewarded = 0; s->wtd = 1;
+  calc_t cs; memset(&cs, 0, sizeof cs);
+  flag_next_target(E, 0, s, 0, &cs, 1);
+  int i = 0;
+  for (; i < n_steps; i++) {
+    s->wtd = (real)wtd[i];
+    real r;
+    int d = flagrun_task(E, 0, s, &cs, (real)inner_r[i], 0, &r);
+    rew[i] = r; done_out[i] = d; target[2 * i] = s->target[0]; target[2 * i + 1] = s->target[1];
+    since[i] = s->since; rewarded[i] = s->rewarded;
+    if (d) { i++; break; }
+  }
+  hrlo_destroy(E);
+  return i;
+}
+
+/* PointBot.calc_state / apply_action and the AntMjEnv.step reward composition (tests/golden/robots.npz) */
+void hrlo_point_state(const double xyz[3], const double rpy[3], const double vel[3], double* out8) {
+  real a[3] = {(real)xyz[0], (real)xyz[1], (real)xyz[2]}, r[3] = {(real)rpy[0], (real)rpy[1], (real)rpy[2]};
+  real v[3] = {(real)vel[0], (real)vel[1], (real)vel[2]}, o[8];
+  point_state_general(a, r, v, 1, o);
+  for (int i = 0; i < 8; i++) out8[i] = o[i];
+}
+void hrlo_point_force(const hrl_config* cfg, const double act[2], double f[3]) {
+  double nn = sqrt(act[0] * act[0] + act[1] * act[1]); /* point_bot.py:29 */
+  f[0] = act[0] / nn * cfg->torque_scale; f[1] = act[1] / nn * cfg->torque_scale; f[2] = 0;
+}
+void hrlo_mj_reward(const hrl_config* cfg, double z, double pot_old, double pot_new, int joints_at_limit, double* rew_done) {
+  /* envs/MjAnt.py:27-28,44,82-97: alive (z > 0.26) + progress + joints_at_limit_cost * count */
+  int alive = z > 0.26;
+  rew_done[0] = (alive ? 1.0 : -1.0) + (pot_new - pot_old) + (double)cfg->joints_at_limit_cost * joints_at_limit;
+  rew_done[1] = !alive;
 }
 
 /* physics diagnostics for invariants tests: total mass, generalized mass matrix via impulse responses */

@@ -59,6 +59,18 @@ def lib(f32=False):
         L.hrlo_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.hrlo_rng_u4.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         L.hrlo_flag_goal.argtypes = [C.POINTER(HrlConfig), C.c_int, C.c_int, C.c_void_p]
+        d = C.c_double
+        L.hrlo_maze_target_sensor.argtypes = [C.c_int, d, d, C.c_int, C.c_void_p, d, d, d, d, d, d, C.c_void_p]
+        L.hrlo_maze_target_sensor.restype = None
+        L.hrlo_maze_task_replay.argtypes = [C.POINTER(HrlConfig), C.c_void_p, C.c_void_p, d, d, C.c_int, d, C.c_void_p, C.c_int,
+                                            C.c_void_p, C.c_void_p]
+        L.hrlo_flagrun_replay.argtypes = [C.POINTER(HrlConfig), C.c_void_p, C.c_int] + [C.c_void_p] * 7
+        L.hrlo_point_state.argtypes = [C.c_void_p] * 4
+        L.hrlo_point_state.restype = None
+        L.hrlo_point_force.argtypes = [C.POINTER(HrlConfig), C.c_void_p, C.c_void_p]
+        L.hrlo_point_force.restype = None
+        L.hrlo_mj_reward.argtypes = [C.POINTER(HrlConfig), d, d, d, C.c_int, C.c_void_p]
+        L.hrlo_mj_reward.restype = None
         _LIBS[key] = L
     return _LIBS[key]
 

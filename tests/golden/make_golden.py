@@ -227,7 +227,8 @@ def gen_gather_step(rng):
     M = 400
     fake = _ref_stubs.FakeBullet()
     res = {}
-    for tag, cls, n_bins, sdim in [("ant", AntGatherBulletEnv, 10, 28), ("point", GatherBulletEnv, 5, 8)]:
+    for tag, cls, n_bins, sdim in [("ant", AntGatherBulletEnv, 10, 28), ("point", GatherBulletEnv, 5, 8),
+                                   ("antabs", AntGatherBulletEnv, 5, 28)]:  # antabs: use_sensor=False -> get_abs_pos
         state = f32(rng.uniform(-1, 1, size=(M, sdim)))
         xyz = f32(np.concatenate([rng.uniform(-7, 7, size=(M, 2)), rng.uniform(0.15, 0.9, size=(M, 1))], axis=1))
         rpy = f32(rng.uniform(-math.pi, math.pi, size=(M, 3)) * [0.2, 0.2, 1.0])
@@ -243,12 +244,12 @@ def gen_gather_step(rng):
             sc.food = {i: [float(objs[m, i, 0]), float(objs[m, i, 1]), 0.1] for i in range(8)}
             sc.poison = {i: [float(objs[m, i, 0]), float(objs[m, i, 1]), 0.1] for i in range(8, 16)}
             sc.rs = ListRNG(u[m])
-            initial_z = 0.75 if tag == "ant" else 1.0
+            initial_z = 0.75 if tag.startswith("ant") else 1.0
             st = state[m].copy()
             st[0] = xyz[m, 2] - initial_z
             torso = NS(get_pose=lambda m=m: [*xyz[m], 0, 0, 0, 1], get_position=lambda m=m: list(xyz[m]),
                        pose=lambda m=m: pose_ns(xyz[m], rpy[m]))
-            if tag == "ant":
+            if tag.startswith("ant"):
                 alive = lambda z, pitch: +1 if z > 0.26 else -1
             else:
                 alive = lambda z, pitch: PointBot.alive_bonus(None, z, pitch)
@@ -256,14 +257,15 @@ def gen_gather_step(rng):
                        alive_bonus=alive, initial_z=initial_z, body_rpy=rpy[m], robot_body=torso, objects=[0])
             stub = NS(robot=robot, scene=NS(global_step=lambda: None), stadium_scene=sc, parts={"torso": torso},
                       robot_body=torso, robot_coll_dist=1, n_bins=n_bins, sensor_span=np.pi, sensor_range=20.0,
-                      use_sensor=True, dying_cost=-10, debug=False, FOOD="food", POISON="poison", _p=fake)
+                      use_sensor=(tag != "antabs"), dying_cost=-10, debug=False, FOOD="food", POISON="poison", _p=fake)
             stub.sq_dist_robot = lambda pos, stub=stub: cls.sq_dist_robot(stub, pos)
             stub.get_food_obs = lambda d, stub=stub: cls.get_food_obs(stub, d)
             stub.get_sensor_readings = lambda d, stub=stub: cls.get_sensor_readings(stub, d)
+            stub.get_abs_pos = lambda d, stub=stub: cls.get_abs_pos(stub, d)
             import warnings
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
-                obs, rew, done, info = cls.step(stub, np.zeros(8 if tag == "ant" else 2))
+                obs, rew, done, info = cls.step(stub, np.zeros(8 if tag.startswith("ant") else 2))
             OBS.append(obs); REW.append(rew); DONE.append(done)
             FR.append(info["food_rew"]); DR.append(info["dead_rew"])
             NEWO.append(np.array([sc.all_items[i][:2] for i in range(16)]))
@@ -288,27 +290,38 @@ def gen_maze_step(rng):
     wtd = f32(rng.uniform(0.5, 4.0, size=M))
     tid = rng.integers(0, 4, size=M)
     targets = np.array(maze_mod._targets, dtype=np.float64)
-    OBS, REW, DONE = [], [], []
-    for m in range(M):
-        class Base(maze_mod.AntBulletEnv):
-            pass
-        # bind a fake inner step onto the stub base class the reference env derives from
-        maze_mod.AntBulletEnv.step = lambda self, a, m=m: (ant_obs[m].astype(np.float32), float(inner_rew[m]),
-                                                          bool(inner_done[m]), {})
-        env = AntMazeBulletEnv.__new__(AntMazeBulletEnv)
-        env.t = 0; env.debug = 0; env.target = targets[tid[m]]; env.inner_rew_weight = 0; env.tol = 1.5
-        env.done_at_target = True; env.max_steps = -1; env.targ_dist_rew = False
-        env.sense_walls = True; env.sense_target = False; env.n_bins = 10; env.sensor_span = 2 * np.pi
-        env.sensor_range = 5.0; env.target_encoding = PositionEncoding.normed_vec
-        env.scene = maze
-        env.robot = NS(walk_target_dist=float(wtd[m]), body_real_xyz=np.array([xy[m, 0], xy[m, 1], 0.5]))
-        env.robot_body = NS(pose=lambda m=m: pose_ns([xy[m, 0], xy[m, 1], 0.5], [0, 0, float(yaw[m])]))
-        obs, rew, done, info = env.step(np.zeros(8))
-        OBS.append(obs); REW.append(rew); DONE.append(done)
+    t_before = rng.integers(0, 9, size=M)  # used by the max_steps variant only
+    # default kwargs first, then the non-default ones (ant_maze_bullet_env.py:23-25)
+    variants = {"": {}, "_sense_target": dict(sense_target=True),
+                "_max_steps": dict(max_steps=7, done_at_target=False),
+                "_targ_dist": dict(targ_dist_rew=True, inner_rew_weight=0.5),
+                "_angle_nowalls": dict(target_encoding=PositionEncoding.angle, sense_walls=False)}
+    res = {}
+    for tag, kw in variants.items():
+        OBS, REW, DONE = [], [], []
+        for m in range(M):
+            # bind a fake inner step onto the stub base class the reference env derives from
+            maze_mod.AntBulletEnv.step = lambda self, a, m=m: (ant_obs[m].astype(np.float32), float(inner_rew[m]),
+                                                              bool(inner_done[m]), {})
+            env = AntMazeBulletEnv.__new__(AntMazeBulletEnv)
+            env.t = int(t_before[m]) if tag == "_max_steps" else 0
+            env.debug = 0; env.target = targets[tid[m]]; env.inner_rew_weight = 0; env.tol = 1.5
+            env.done_at_target = True; env.max_steps = -1; env.targ_dist_rew = False
+            env.sense_walls = True; env.sense_target = False; env.n_bins = 10; env.sensor_span = 2 * np.pi
+            env.sensor_range = 5.0; env.target_encoding = PositionEncoding.normed_vec
+            for k, v in kw.items():
+                setattr(env, k, v)
+            env.scene = maze
+            env.robot = NS(walk_target_dist=float(wtd[m]), body_real_xyz=np.array([xy[m, 0], xy[m, 1], 0.5]))
+            env.robot_body = NS(pose=lambda m=m: pose_ns([xy[m, 0], xy[m, 1], 0.5], [0, 0, float(yaw[m])]))
+            obs, rew, done, info = env.step(np.zeros(8))
+            OBS.append(obs); REW.append(rew); DONE.append(done)
+        res.update({"obs" + tag: np.array(OBS, dtype=np.float64), "rew" + tag: np.array(REW, dtype=np.float64),
+                    "done" + tag: np.array(DONE)})
+    res["t_before_max_steps"] = t_before
     del maze_mod.AntBulletEnv.step
     np.savez_compressed(os.path.join(HERE, "maze_step.npz"), ant_obs=ant_obs, xy=xy, yaw=yaw, inner_rew=inner_rew,
-             inner_done=inner_done, wtd=wtd, tid=tid, targets=targets, obs=np.array(OBS, dtype=np.float64),
-             rew=np.array(REW, dtype=np.float64), done=np.array(DONE))
+             inner_done=inner_done, wtd=wtd, tid=tid, targets=targets, **res)
 
 
 # --------------------------------------------------------------------------- 9. Flagrun.step sequence
@@ -322,10 +335,10 @@ def gen_flagrun_step(rng):
     wtd[rng.uniform(size=T) < 0.85] += 1.0  # mostly far from the goal
     inner_r = f32(rng.uniform(-1, 1, size=T))
     seqs = {}
-    for tag, n_goals, timeout in [("a", 100, 200), ("b", 3, 50)]:
+    for tag, n_goals, timeout, switch in [("a", 100, 200, True), ("b", 3, 50, True), ("c", 5, 40, False)]:
         env = AntFlagrunBulletEnv.__new__(AntFlagrunBulletEnv)
         env.size = 10; env.tol = 0.5; env.max_targets = n_goals; env.max_target_dist = 0; env.timeout = timeout
-        env.switch_flag_on_collision = True; env.debug = False; env.use_sensor = False; env.isRender = False
+        env.switch_flag_on_collision = switch; env.debug = False; env.use_sensor = False; env.isRender = False
         env.flag = None
         env.mpi_common_rand = np.random.RandomState(123)
         env.create_target()
@@ -353,7 +366,8 @@ def gen_flagrun_step(rng):
         del fr_mod.AntBulletEnv.step
         seqs.update({f"{tag}_goals0": goals0, f"{tag}_first_target": first_target, f"{tag}_rew": np.array(R),
                      f"{tag}_done": np.array(D), f"{tag}_target": np.array(TG), f"{tag}_since": np.array(SS),
-                     f"{tag}_rewarded": np.array(RW), f"{tag}_n_goals": n_goals, f"{tag}_timeout": timeout})
+                     f"{tag}_rewarded": np.array(RW), f"{tag}_n_goals": n_goals, f"{tag}_timeout": timeout,
+                     f"{tag}_switch": int(switch)})
     np.savez_compressed(os.path.join(HERE, "flagrun_step.npz"), wtd=wtd, inner_r=inner_r, **seqs)
 
 

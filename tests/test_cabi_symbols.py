@@ -65,9 +65,23 @@ def test_kwargs_mapping():
     assert tuple(cfg.world_size) == (11.0, 13.0)
     with pytest.raises(TypeError):
         K.apply_kwargs(cfg, K.HRL_ANT_GATHER, dict(nonsense=1))
+    K.apply_kwargs(cfg, K.HRL_ANT_GATHER, dict(use_sensor=False))      # get_abs_pos: xy of the nearest items
+    assert cfg.use_sensor == 0 and K.obs_dim(cfg) == 26 + 2 * 3 + 2 * 2
+    with pytest.raises(NotImplementedError):                             # still outside the built scope: fail loudly
+        K.apply_kwargs(cfg, K.HRL_ANT_GATHER, dict(robot_coll_dist=0))
+    p = _cabi.default_config(K.HRL_POINT_GATHER, 1)
     with pytest.raises(NotImplementedError):
-        K.apply_kwargs(cfg, K.HRL_ANT_GATHER, dict(use_sensor=False))
+        K.apply_kwargs(p, K.HRL_POINT_GATHER, dict(use_sensor=False))
+    f = _cabi.default_config(K.HRL_ANT_FLAGRUN, 1)
+    K.apply_kwargs(f, K.HRL_ANT_FLAGRUN, dict(use_sensor=True, sensor_bins=6, switch_flag_on_collision=False))
+    assert f.flag_use_sensor == 1 and f.flag_switch_on_collision == 0 and K.obs_dim(f) == 34
+    with pytest.raises(AssertionError):                                  # ant_flagrun_env.py:17-18
+        K.apply_kwargs(_cabi.default_config(K.HRL_ANT_FLAGRUN, 1), K.HRL_ANT_FLAGRUN, dict(max_target_dist=3.0))
+    with pytest.raises(NotImplementedError):
+        K.apply_kwargs(_cabi.default_config(K.HRL_ANT_FLAGRUN, 1), K.HRL_ANT_FLAGRUN, dict(manual_goal_creation=True))
     m = _cabi.default_config(K.HRL_ANT_MAZE, 1)
     K.apply_kwargs(m, K.HRL_ANT_MAZE, dict(targets=([1, 2], [3, 4]), tol=2.0, target_encoding=1))
     assert m.n_targets == 2 and m.targets[1][0] == 3.0 and m.tol == 2.0 and m.target_encoding == 1
     assert K.obs_dim(m) == 38
+    K.apply_kwargs(m, K.HRL_ANT_MAZE, dict(sense_target=True, max_steps=50, targ_dist_rew=True))
+    assert (m.sense_target, m.maze_max_steps, m.targ_dist_rew) == (1, 50, 1) and K.obs_dim(m) == 46

@@ -320,3 +320,54 @@ def test_gym_surface():
             obs, rew, done, info = env.step(env.action_space.sample())
         assert obs.shape == (D,) and isinstance(rew, float) and isinstance(done, bool)
         env.close()
+
+
+# ------------------------------------------------------------------ non-default ctor kwargs
+KWARG_CASES = [
+    ("AntGatherBulletEnv-v0", dict(use_sensor=False, n_bins=5)),            # get_abs_pos, ant_gather_env.py:179-196
+    ("AntGatherBulletEnv-v0", dict(respawn=False, n_bins=6, sensor_range=12.0)),
+    ("AntMazeBulletEnv-v0", dict(sense_target=True)),                       # ant_maze_bullet_env.py:135-178
+    ("AntMazeBulletEnv-v0", dict(max_steps=20, done_at_target=False, targ_dist_rew=True, inner_rew_weight=0.3)),
+    ("AntMazeBulletEnv-v0", dict(target_encoding=1, sense_walls=False, tol=3.0)),
+    ("AntFlagrunBulletEnv-v0", dict(use_sensor=True)),                      # ant_flagrun_env.py:122-130
+    ("AntFlagrunBulletEnv-v0", dict(switch_flag_on_collision=False, timeout=15, max_targets=3, tolerance=2.5)),
+    ("AntFlagrunBulletEnv-v0", dict(max_targets=0, max_target_dist=4.0, tolerance=1.5, timeout=10)),  # create_close_target :80-89
+]
+
+
+@pytest.mark.parametrize("env_id,kw", KWARG_CASES, ids=["%s-%s" % (e[:8], "+".join(sorted(k))) for e, k in KWARG_CASES])
+def test_kwargs_one_step_parity(env_id, kw):
+    """Every non-default constructor kwarg that is built: reset + one-step parity from identical saved
+    states against the oracle (whose task layer is pinned on the reference by tests/test_oracle_golden.py)."""
+    N, T = 256, 60
+    g, o = _envs(env_id, N, seed=21, **kw)
+    assert g.D == o.D
+    og = g.reset().cpu().numpy(); oo = o.reset()
+    np.testing.assert_allclose(og, oo, rtol=0, atol=2e-5)
+    gen = torch.Generator().manual_seed(3)
+    checked = n_out = 0
+    nsens = {"AntGatherBulletEnv-v0": 26}.get(env_id)
+    for t in range(T):
+        a = torch.rand(N, g.A, generator=gen) * 2 - 1
+        f, i = g.get_state()
+        o.set_state(f.cpu().numpy().astype(np.float64), i.cpu().numpy())
+        og, rg, dg, info = g.step(a.cuda())
+        oo, ro, do, io = o.step(a.numpy())
+        dg = dg.cpu().numpy(); rg = rg.cpu().numpy(); og = og.cpu().numpy()
+        f2, i2 = g.get_state(); fo, io2 = o.get_state()
+        same = dg == do
+        live = same & ~dg
+        ep, ev = _state_err(f2.cpu().numpy()[live], fo[live])
+        ok = (ep < POS_TOL) & (ev < VEL_TOL)
+        idx = np.nonzero(live)[0][ok]
+        n_out += int((~ok).sum()) + int((~same).sum()); checked += int(live.sum())
+        cols = slice(0, nsens) if nsens else slice(None)
+        # lidar / goal readings are continuous in the pose; gather readings (bin flips) are excluded like above
+        assert np.abs(og[idx][:, cols] - oo[idx][:, cols]).max(initial=0) < 2e-2
+        if env_id != "AntFlagrunBulletEnv-v0":   # progress reward amplifies 1e-3 m by 1/dt
+            assert np.abs(rg[idx] - ro[idx]).max(initial=0) <= max(REW_TOL, 2e-3 * float(kw.get("targ_dist_rew", 0)))
+        fin = same & dg   # finished envs reset to the same new episode (targets, goal counters)
+        assert np.array_equal(i2.cpu().numpy()[fin], io2[fin])
+        np.testing.assert_allclose(f2.cpu().numpy()[fin][:, K.SF_TARGET:K.SF_TARGET + 2], fo[fin][:, K.SF_TARGET:K.SF_TARGET + 2], atol=1e-4)
+    assert checked > 0.5 * N * T or "max_steps" in kw
+    assert n_out <= 5e-3 * max(checked, 1) + 2, (n_out, checked)

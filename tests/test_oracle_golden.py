@@ -79,22 +79,25 @@ def test_random_on_plane(golden):
     assert list(g["parked"]) == [100, 0, -10]
 
 
-@pytest.mark.parametrize("tag,kind,nbase,can_die", [("ant", K.HRL_ANT_GATHER, 26, 1), ("point", K.HRL_POINT_GATHER, 8, 0)])
+@pytest.mark.parametrize("tag,kind,nbase,can_die", [("ant", K.HRL_ANT_GATHER, 26, 1), ("point", K.HRL_POINT_GATHER, 8, 0),
+                                                    ("antabs", K.HRL_ANT_GATHER, 26, 1)])
 def test_gather_step_task_layer(golden, tag, kind, nbase, can_die):
     """Whole reference AntGather/PointGather `step` task layer (pickups, respawn rule with
     replayed uniforms, sensor, alive/done, reward, info)."""
     g = golden("gather_step.npz")
     L = O.lib()
     cfg = O.default_config(kind, 1)
-    nb = cfg.n_bins
+    if tag == "antabs":  # use_sensor=False: xy of the n_bins nearest food / poison items (ant_gather_env.py:179-196)
+        cfg.use_sensor = 0; cfg.n_bins = 5
+    nb = K.food_obs_dim(cfg) // 2
     bad = 0
     for m in range(len(g[f"{tag}_state"])):
         st = g[f"{tag}_state"][m].copy()
         xyz = g[f"{tag}_xyz"][m]
-        st[0] = np.float32(xyz[2] - (0.75 if tag == "ant" else 1.0))
+        st[0] = np.float32(xyz[2] - (0.75 if tag.startswith("ant") else 1.0))
         st = st.astype(np.float32).astype(np.float64)
-        base = np.ascontiguousarray(np.concatenate([st[0:1], st[3:]]) if tag == "ant" else st)
-        z_alive = st[0] + (0.75 if tag == "ant" else 1.0)
+        base = np.ascontiguousarray(np.concatenate([st[0:1], st[3:]]) if tag.startswith("ant") else st)
+        z_alive = st[0] + (0.75 if tag.startswith("ant") else 1.0)
         items = np.ascontiguousarray(g[f"{tag}_objs"][m].reshape(-1).copy())
         u = np.ascontiguousarray(g[f"{tag}_u"][m])
         obs = np.zeros(nbase + 2 * nb); rdi = np.zeros(4); used = O.C.c_int(0)
@@ -119,3 +122,122 @@ def test_registry():
                    "PointGatherBulletEnv-v0"}
     assert all(r["max_episode_steps"] == 2000 for r in reg)
     assert ids <= set(K.ENV_IDS)
+
+
+# ---------------------------------------------------------------- maze goal observations (maze_target.npz)
+def test_maze_target_vec_and_sensor(golden):
+    """get_target_vec_obs (both encodings) and get_target_sensor_obs (range, box occlusion, bin)
+    of ant_maze_bullet_env.py:123-178 on 300 poses."""
+    g = golden("maze_target.npz")
+    L = O.lib()
+    cfg = O.default_config(K.HRL_ANT_MAZE, 1)
+    box = np.ascontiguousarray(O.scene_bounds(cfg)[4:7])
+    assert box.shape == (3, 4)
+    for m in range(len(g["xy"])):
+        xy = g["xy"][m].astype(np.float64); yaw = float(g["yaw"][m]); tgt = g["targets"][g["tid"][m]].astype(np.float64)
+        rd = np.zeros(10)
+        L.hrlo_maze_target_sensor(10, 2 * np.pi, 5.0, 3, O._p(box), xy[0], xy[1], yaw, tgt[0], tgt[1], float(g["wtd"][m]), O._p(rd))
+        np.testing.assert_allclose(rd, g["sensor"][m], rtol=0, atol=1e-12)
+        for enc, key in ((0, "vec_normed"), (1, "vec_angle")):
+            c = cfg.copy(); c.target_encoding = enc
+            obs = np.zeros(38); rd2 = np.zeros(2)
+            L.hrlo_maze_task_replay(O.C.byref(c), O._p(np.zeros(28)), O._p(np.ascontiguousarray(xy)), yaw, 0.0, 0, float(g["wtd"][m]),
+                                    O._p(np.ascontiguousarray(tgt)), 0, O._p(obs), O._p(rd2))
+            np.testing.assert_allclose(obs[26:28], g[key][m], rtol=0, atol=1e-12)
+    assert g["sensor"][0][7] == pytest.approx(0.6) and not g["sensor"][1].any()  # SURVEY.md 8c known answers
+
+
+# ---------------------------------------------------------------- whole Maze step task layer (maze_step*.npz)
+def _maze_cfg(variant):
+    cfg = O.default_config(K.HRL_ANT_MAZE, 1)
+    for k, v in variant.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+@pytest.mark.parametrize("tag", ["", "_sense_target", "_max_steps", "_targ_dist", "_angle_nowalls"])
+def test_maze_step_task_layer(golden, tag):
+    """AntMazeBulletEnv.step with a stub inner walker step: observation (goal part + lidar), reward, done
+    (ant_maze_bullet_env.py:63-97) for the default kwargs and the non-default ones."""
+    g = golden("maze_step.npz")
+    if "obs" + tag not in g:
+        pytest.skip("variant not in the fixture")
+    L = O.lib()
+    variant = {"": {}, "_sense_target": {"sense_target": 1},
+               "_max_steps": {"maze_max_steps": 7, "done_at_target": 0},
+               "_targ_dist": {"targ_dist_rew": 1, "inner_rew_weight": 0.5},
+               "_angle_nowalls": {"target_encoding": 1, "sense_walls": 0}}[tag]
+    cfg = _maze_cfg(variant)
+    D = L.hrlo_obs_dim(O.C.byref(cfg))
+    tb = g["t_before" + tag] if "t_before" + tag in g else np.zeros(len(g["xy"]), int)
+    for m in range(len(g["xy"])):
+        obs = np.zeros(D); rd = np.zeros(2)
+        tgt = np.ascontiguousarray(g["targets"][g["tid"][m]].astype(np.float64))
+        L.hrlo_maze_task_replay(O.C.byref(cfg), O._p(np.ascontiguousarray(g["ant_obs"][m].astype(np.float64))),
+                                O._p(np.ascontiguousarray(g["xy"][m].astype(np.float64))), float(g["yaw"][m]),
+                                float(g["inner_rew"][m]), int(g["inner_done"][m]), float(g["wtd"][m]), O._p(tgt), int(tb[m]),
+                                O._p(obs), O._p(rd))
+        want = g["obs" + tag][m]
+        assert want.shape == (D,)
+        np.testing.assert_allclose(obs, want, rtol=0, atol=1e-12)
+        assert rd[0] == pytest.approx(g["rew" + tag][m], abs=1e-12) and bool(rd[1]) == bool(g["done" + tag][m])
+
+
+# ---------------------------------------------------------------- Flagrun step sequences (flagrun_step.npz)
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_flagrun_step_sequence(golden, tag):
+    """AntFlagrunBulletEnv.step bookkeeping (ant_flagrun_env.py:162-204) on a scripted sequence: +5000 once
+    per goal, goals popped from the END of the list, 200-step timeout, IndexError -> done, the
+    switch_flag_on_collision kwarg (sequence c)."""
+    g = golden("flagrun_step.npz")
+    if tag + "_rew" not in g:
+        pytest.skip("variant not in the fixture")
+    L = O.lib()
+    cfg = O.default_config(K.HRL_ANT_FLAGRUN, 1)
+    cfg.flag_max_targets = int(g[tag + "_n_goals"]); cfg.flag_timeout = int(g[tag + "_timeout"])
+    if tag + "_switch" in g:
+        cfg.flag_switch_on_collision = int(g[tag + "_switch"])
+    goals = np.ascontiguousarray(g[tag + "_goals0"].astype(np.float64))
+    T = len(g["wtd"])
+    rew = np.zeros(T); done = np.zeros(T, np.int32); tg = np.zeros((T, 2)); since = np.zeros(T, np.int32); rw = np.zeros(T, np.int32)
+    n = L.hrlo_flagrun_replay(O.C.byref(cfg), O._p(goals), T, O._p(np.ascontiguousarray(g["wtd"].astype(np.float64))),
+                              O._p(np.ascontiguousarray(g["inner_r"].astype(np.float64))), O._p(rew), O._p(done), O._p(tg),
+                              O._p(since), O._p(rw))
+    assert n == len(g[tag + "_rew"])
+    np.testing.assert_allclose(rew[:n], g[tag + "_rew"], rtol=0, atol=1e-9)
+    assert np.array_equal(done[:n].astype(bool), g[tag + "_done"])
+    np.testing.assert_allclose(tg[:n], g[tag + "_target"], rtol=0, atol=1e-12)
+    assert np.array_equal(since[:n], g[tag + "_since"]) and np.array_equal(rw[:n].astype(bool), g[tag + "_rewarded"])
+
+
+def test_flagrun_goal_rule(golden):
+    """create_target (ant_flagrun_env.py:71-78): the reference's MT19937 stream is not reproduced (DESIGN.md
+    section 2), the placement rule is: uniform on the size^2 square, never closer than 0.5 to the origin."""
+    g = golden("flagrun_goals.npz")
+    for key in ("goals1", "goals2"):
+        G = g[key]
+        assert G.shape == (100, 2) and (np.abs(G) <= 5).all() and (np.linalg.norm(G, axis=1) >= 0.5).all()
+    cfg = O.default_config(K.HRL_ANT_FLAGRUN, 1)
+    ours = np.zeros((100, 2))
+    for j in range(100):
+        gj = np.zeros(2); O.lib().hrlo_flag_goal(O.C.byref(cfg), 3, j, O._p(gj)); ours[j] = gj
+    assert (np.abs(ours) <= 5).all() and (np.linalg.norm(ours, axis=1) >= 0.5).all()
+    assert abs(ours.mean()) < 1.0 and 2.0 < ours.std() < 3.6  # U(-5,5): std 2.89
+
+
+# ---------------------------------------------------------------- PointBot + AntMjEnv reward (robots.npz)
+def test_pointbot_and_mj_reward(golden):
+    g = golden("robots.npz")
+    L = O.lib()
+    cfgp = O.default_config(K.HRL_POINT_GATHER, 1); cfgm = O.default_config(K.HRL_ANT_MJ, 1)
+    for m in range(len(g["xyz"])):
+        out = np.zeros(8)
+        L.hrlo_point_state(O._p(np.ascontiguousarray(g["xyz"][m].astype(np.float64))), O._p(np.ascontiguousarray(g["rpy"][m].astype(np.float64))),
+                           O._p(np.ascontiguousarray(g["vel"][m].astype(np.float64))), O._p(out))
+        np.testing.assert_allclose(out, g["point_state"][m], rtol=0, atol=2e-6)  # the reference returns float32
+        f = np.zeros(3)
+        L.hrlo_point_force(O.C.byref(cfgp), O._p(np.ascontiguousarray(g["act"][m].astype(np.float64))), O._p(f))
+        np.testing.assert_allclose(f, g["force"][m], rtol=1e-6, atol=1e-4)
+        rd = np.zeros(2)
+        L.hrlo_mj_reward(O.C.byref(cfgm), float(g["mj_state"][m, 2]), float(g["pot_old"][m]), float(g["pot_new"][m]), int(g["jal"][m]), O._p(rd))
+        assert rd[0] == pytest.approx(g["mj_rew"][m], abs=1e-5) and bool(rd[1]) == bool(g["mj_done"][m])
