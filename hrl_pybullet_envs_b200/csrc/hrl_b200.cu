@@ -1109,6 +1109,7 @@ static void* mapped_alias(hrl_handle* h, const void* p) {
 int hrl_set_host_mode(hrl_handle* h, int32_t mode) {
   if (!h || mode < HRL_HOST_AUTO || mode > HRL_HOST_ZEROCOPY) return set_err(HRL_E_INVALID, "bad argument to hrl_set_host_mode");
   h->host_mode = mode;
+  h->alias_n = 0;  // also forgets the cached pinned-buffer aliases (call this after freeing such a buffer)
   return HRL_OK;
 }
 

@@ -169,7 +169,10 @@ int hrl_step_host(hrl_handle* h, const float* h_actions, float* h_obs, float* h_
  *                      buffers are carved out of one allocation as hrl_host_layout says), sync;
  *   HRL_HOST_ZEROCOPY  every buffer must be pinned: the kernel reads / writes them over PCIe while
  *                      it computes (transfers overlap the step), sync;
- *   HRL_HOST_AUTO      zero-copy when all buffers are pinned, else copy (default). */
+ *   HRL_HOST_AUTO      zero-copy when all buffers are pinned, else copy (default).
+ * The handle caches which host pointers are pinned; calling hrl_set_host_mode (any mode) clears
+ * that cache - do so after freeing a pinned buffer that was passed to hrl_step_host.
+ * Calls on one handle must not overlap (the reference env is single-threaded too). */
 #define HRL_HOST_AUTO 0
 #define HRL_HOST_COPY 1
 #define HRL_HOST_ZEROCOPY 2
