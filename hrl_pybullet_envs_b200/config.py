@@ -46,6 +46,7 @@ class HrlConfig(C.Structure):
         ("electricity_cost", C.c_float), ("stall_torque_cost", C.c_float), ("joints_at_limit_cost", C.c_float),
         ("sense_target", C.c_int32), ("maze_max_steps", C.c_int32), ("targ_dist_rew", C.c_int32),
         ("flag_use_sensor", C.c_int32), ("flag_switch_on_collision", C.c_int32), ("flag_max_target_dist", C.c_float),
+        ("item_contacts", C.c_int32), ("item_friction", C.c_float), ("item_half", C.c_float), ("item_z", C.c_float),
     ]
 
     def copy(self):
@@ -94,8 +95,14 @@ def apply_kwargs(cfg, kind, kw):
             cfg.use_sensor = int(bool(kw.pop("use_sensor")))  # False: get_abs_pos, ant_gather_env.py:179-196
             if not cfg.use_sensor and kind == HRL_POINT_GATHER:
                 raise NotImplementedError(_UNSUPPORTED % ("use_sensor", False))
-        if cfg.robot_coll_dist <= 0:
-            raise NotImplementedError(_UNSUPPORTED % ("robot_coll_dist", cfg.robot_coll_dist))
+        if "item_contacts" in kw:      # extension kwarg: switch the cube colliders (default on for AntGather) off / on
+            cfg.item_contacts = int(bool(kw.pop("item_contacts")))
+            if kind == HRL_POINT_GATHER and cfg.item_contacts:
+                raise NotImplementedError(_UNSUPPORTED % ("item_contacts", True))
+        if cfg.robot_coll_dist <= 0:  # contact-based pickup (ant_gather_env.py:113-116): the cubes must be colliders
+            if kind == HRL_POINT_GATHER:
+                raise NotImplementedError(_UNSUPPORTED % ("robot_coll_dist", cfg.robot_coll_dist))
+            cfg.item_contacts = 1
     elif kind in (HRL_ANT_MAZE, HRL_ANT_MAZE_MJ):
         if "n_bins" in kw:
             cfg.n_bins = int(kw.pop("n_bins"))

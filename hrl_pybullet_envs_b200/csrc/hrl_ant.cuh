@@ -36,12 +36,16 @@
 #define HRL_ROWS_ENV (8 + 12 * HRL_MAXC)
 #define HRL_ROW_IDLE (HRL_ROWS_ENV + 1)        // rows ROWS_ENV, ROWS_ENV+1: all-zero rows / zero impulses for idle visits
 #define HRL_ENV_F4 ((HRL_ROWS_ENV + 2) * 4 + 1)  // float4 per env, +1: the env stride maps the 8 envs of a warp to distinct banks
-#define HRL_LAM_STRIDE (HRL_ROWS_ENV + 3)      // odd: the 8 envs of a warp hit distinct banks
+#define HRL_MU0 (HRL_ROWS_ENV + 2)             // per-contact friction coefficient mu[4*MAXC], in the same array as the impulses
+#define HRL_LAM_STRIDE (HRL_ROWS_ENV + 2 + 4 * HRL_MAXC + 1)  // odd: the 8 envs of a warp hit distinct banks
 #define HRL_ROWS_FLOATS_PER_WARP (HRL_EPW * HRL_ENV_F4 * 4)
 #define HRL_LAM_FLOATS_PER_WARP ((HRL_EPW * HRL_LAM_STRIDE + 3) / 4 * 4)
 // contact candidates: [c][field][lane]: P-O (3), n (3), dist, body
 #define HRL_CAND_F 8
 #define HRL_SMEM_FLOATS_PER_WARP (HRL_ROWS_FLOATS_PER_WARP + HRL_LAM_FLOATS_PER_WARP + HRL_MAXC * HRL_CAND_F * 32)
+
+// food / poison cube colliders (hrl_config.item_contacts): per-warp scratch [EPW][16] (x, y) + [EPW][16] contact-point counters
+#define HRL_ITEM_SCRATCH_FLOATS (HRL_EPW * 16 * 3)
 
 struct AntLane {
   // replicated in the 4 lanes of an env
@@ -151,6 +155,8 @@ struct SubstepParams {
   float wx, wy;  // wall inner faces at +-wx, +-wy
   int has_walls, has_box, iters;
   float blo[3], bhi[3];
+  int item_contacts, n_items;  // cube colliders (AntGather only)
+  float mu_item, item_half, item_z;
 };
 
 __device__ __forceinline__ SubstepParams make_params(const hrl_config& cfg) {
@@ -160,6 +166,8 @@ __device__ __forceinline__ SubstepParams make_params(const hrl_config& cfg) {
   p.vmax = cfg.max_coord_vel; p.margin = cfg.contact_margin; p.gz = cfg.ground_z;
   p.wx = cfg.world_size[0] * 0.5f - 0.05f; p.wy = cfg.world_size[1] * 0.5f - 0.05f;
   p.has_walls = cfg.has_walls; p.has_box = cfg.has_box; p.iters = cfg.solver_iters;
+  p.item_contacts = cfg.item_contacts && cfg.env_kind == HRL_ANT_GATHER; p.n_items = cfg.n_food + cfg.n_poison;
+  p.mu_item = cfg.item_friction; p.item_half = cfg.item_half; p.item_z = cfg.item_z;
 #pragma unroll
   for (int i = 0; i < 3; i++) { p.blo[i] = cfg.box_lo[i]; p.bhi[i] = cfg.box_hi[i]; }
   return p;
@@ -276,9 +284,14 @@ __device__ __forceinline__ void pair_visit(float* __restrict__ lamp, float2 dv[7
 // (rows: HRL_ROWS_FLOATS_PER_WARP row floats followed by HRL_LAM_FLOATS_PER_WARP impulses).
 // feet_ground: bit set when this leg's foot link (tip or ankle sphere) has a floor manifold at
 // the START of the sub-step (collision detection precedes the dynamics, like Bullet).
+// ITEMS: compile the food / poison cube colliders in (AntGather).  it_x / it_y: this lane's 4 items (4k..4k+3);
+// iscr: HRL_ITEM_SCRATCH_FLOATS floats of this warp; count_touch: tally contact points per cube (last sub-step).
+template <bool ITEMS>
 __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, const LegConst& lc, float tau1,
                                             float tau2, float* __restrict__ rows, float* __restrict__ cands,
-                                            int lane, int k, int es, int& feet_ground, int& stat_contacts, int& stat_limits) {
+                                            int lane, int k, int es, int& feet_ground, int& stat_contacts, int& stat_limits,
+                                            const float* it_x = nullptr, const float* it_y = nullptr, float* iscr = nullptr,
+                                            bool count_touch = false) {
   const LegKin K = leg_fk(s, lc);
   const V3 a1 = K.ez, a2 = K.a2;
   const V3 r_ac = K.rh + K.r1;           // aux COM - O
@@ -294,6 +307,26 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
     // candidate order inside the group: [torso sphere (lane 0)], tip (foot), ankle (aux), hip (torso);
     // per sphere: ground, walls +x -x +y -y, box.  Rolled on purpose (code size); the four wall tests
     // hide behind one comparison because a wall contact is rare.
+    // cube colliders: cubes within reach of the robot (torso-distance cull: longest reach 1.131 m + half + r + margin
+    // per axis) are staged in shared memory with a 16-bit candidate mask per env; usually the mask is empty
+    unsigned imask = 0;
+    float* ixy = nullptr;
+    int* itouch = nullptr;
+    if (ITEMS && P.item_contacts) {
+      ixy = iscr + es * 32; itouch = reinterpret_cast<int*>(iscr + HRL_EPW * 32) + es * 16;
+      const float reach = 1.1314f + 1.4143f * (P.item_half + ant::R_CAPS + P.margin);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int gi = 4 * k + i;
+        const float dx = it_x[i] - s.O.x, dy = it_y[i] - s.O.y;
+        if (gi < P.n_items && dx * dx + dy * dy < reach * reach) imask |= 1u << gi;
+        ixy[2 * gi] = it_x[i]; ixy[2 * gi + 1] = it_y[i];
+        if (count_touch) itouch[gi] = 0;
+      }
+      imask |= __shfl_xor_sync(HRL_FULL_MASK, imask, 1);
+      imask |= __shfl_xor_sync(HRL_FULL_MASK, imask, 2);
+      __syncwarp();
+    }
     auto add = [&](V3 crel, float r, V3 n, float dist, float body) {
       if (nC < HRL_MAXC) {
         const V3 Prel = crel - r * n;  // contact point on the robot, relative to O
@@ -350,6 +383,44 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
           dist = -best - r;
         }
         if (dist < P.margin) add(crel, r, n, dist, body);
+      }
+      if (ITEMS) {
+        for (unsigned m = imask; m; m &= m - 1) {  // candidate cubes in index order, after ground / walls like the oracle
+          const int gi = __ffs(m) - 1;
+          const float bx = ixy[2 * gi], by = ixy[2 * gi + 1], hh = P.item_half, rr = hh + r + P.margin;
+          if (fabsf(c.x - bx) > rr || fabsf(c.y - by) > rr) continue;
+          const float lo[3] = {bx - hh, by - hh, P.item_z - hh}, hi[3] = {bx + hh, by + hh, P.item_z + hh};
+          const float cc[3] = {c.x, c.y, c.z};
+          float qq[3];
+          bool inside = true;
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            float xx = cc[i];
+            if (xx < lo[i]) { xx = lo[i]; inside = false; }
+            if (xx > hi[i]) { xx = hi[i]; inside = false; }
+            qq[i] = xx;
+          }
+          V3 n; float dist;
+          if (!inside) {
+            const V3 d = mk(cc[0] - qq[0], cc[1] - qq[1], cc[2] - qq[2]);
+            const float len = sqrtf(dot(d, d));
+            n = (1.0f / len) * d; dist = len - r;
+          } else {
+            float best = 1e30f; int bi = 0; float bs = 1.f;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+              const float dl = cc[i] - lo[i], dh = hi[i] - cc[i];
+              if (dl < best) { best = dl; bi = i; bs = -1.f; }
+              if (dh < best) { best = dh; bi = i; bs = 1.f; }
+            }
+            n = mk(bi == 0 ? bs : 0.f, bi == 1 ? bs : 0.f, bi == 2 ? bs : 0.f);
+            dist = -best - r;
+          }
+          if (dist < P.margin) {
+            if (count_touch) atomicAdd(&itouch[gi], 1);
+            add(crel, r, n, dist, body + 4.f);  // +4: friction class of the cubes
+          }
+        }
       }
     }
   }
@@ -536,11 +607,14 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
   for (int c = 0; c < nC; c++) {
     const V3 Pr = mk(CAND(c, 0), CAND(c, 1), CAND(c, 2));
     const V3 n = mk(CAND(c, 3), CAND(c, 4), CAND(c, 5));
-    const float dist = CAND(c, 6), body = CAND(c, 7);
+    const float dist = CAND(c, 6), bodyc = CAND(c, 7);
+    const bool cube = ITEMS && bodyc >= 4.f;
+    const float body = cube ? bodyc - 4.f : bodyc;
     V3 t1, t2;
     plane_space(n, t1, t2);
     const V3 Ph = Pr - K.rh, Pa = Pr - r_ank;
     const int ci = offC + c;
+    lamp[HRL_MU0 + ci] = cube ? P.mu_item : P.mu;
 #pragma unroll 1
     for (int di = 0; di < 3; di++) {
       const V3 d = di == 0 ? n : (di == 1 ? t1 : t2);
@@ -604,16 +678,17 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
         int r0 = HRL_FRI_ROW(0), r1;
         Row A0 = ld_row(rb, r0), B0 = ld_row(rb, r0 + 1), A1, B1;
         float n0 = lamp[HRL_NRM_ROW(0)], a0 = lamp[r0], b0 = lamp[r0 + 1], n1, a1, b1;
+        float m0 = lamp[HRL_MU0], m1;  // mu of contact t (slots of idle contacts are never read with lambda_n > 0)
         int t = 0;
         for (; t + 1 < maxNC; t += 2) {
           r1 = HRL_FRI_ROW(t + 1); A1 = ld_row(rb, r1); B1 = ld_row(rb, r1 + 1);
-          n1 = lamp[HRL_NRM_ROW(t + 1)]; a1 = lamp[r1]; b1 = lamp[r1 + 1];
-          pair_visit(lamp, dv, A0, B0, n0, a0, b0, r0, P.mu);
+          n1 = lamp[HRL_NRM_ROW(t + 1)]; a1 = lamp[r1]; b1 = lamp[r1 + 1]; m1 = lamp[HRL_MU0 + t + 1];
+          pair_visit(lamp, dv, A0, B0, n0, a0, b0, r0, m0);
           r0 = HRL_FRI_ROW(t + 2); A0 = ld_row(rb, r0); B0 = ld_row(rb, r0 + 1);
-          n0 = lamp[HRL_NRM_ROW(t + 2)]; a0 = lamp[r0]; b0 = lamp[r0 + 1];
-          pair_visit(lamp, dv, A1, B1, n1, a1, b1, r1, P.mu);
+          n0 = lamp[HRL_NRM_ROW(t + 2)]; a0 = lamp[r0]; b0 = lamp[r0 + 1]; m0 = lamp[HRL_MU0 + min(t + 2, 4 * HRL_MAXC - 1)];
+          pair_visit(lamp, dv, A1, B1, n1, a1, b1, r1, m1);
         }
-        if (t < maxNC) pair_visit(lamp, dv, A0, B0, n0, a0, b0, r0, P.mu);
+        if (t < maxNC) pair_visit(lamp, dv, A0, B0, n0, a0, b0, r0, m0);
       }
     }
   }

@@ -204,6 +204,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
   // ---- physics ----
   float act1 = 0.f, act2 = 0.f;
   int feet_ground = 0;
+  int touch[4] = {0, 0, 0, 0};
   if (mode <= 1) {
     // the branch-free solver multiplies idle (stale) rows by 0: they must be finite
     for (int i = lane; i < (HRL_ROWS_FLOATS_PER_WARP + HRL_LAM_FLOATS_PER_WARP) / 4; i += 32)
@@ -219,7 +220,17 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
     const int ns = mode == 0 ? cfg.substeps : n_sub;
     for (int i = 0; i < ns; i++) {
       const bool on = (i == 0) || !cfg.torque_first_substep_only;
-      ant_substep(s, P, lc, on ? tau1 : 0.f, on ? tau2 : 0.f, rows, cands, lane, k, es, feet_ground, sc, sl);
+      // cube colliders (FAMILY 0): scratch = the sensor-bin area, idle until the task layer; the contact points of
+      // the LAST sub-step are what getContactPoints reports (ant_gather_env.py:114)
+      ant_substep<FAMILY == 0>(s, P, lc, on ? tau1 : 0.f, on ? tau2 : 0.f, rows, cands, lane, k, es, feet_ground, sc, sl, it_x, it_y,
+                               reinterpret_cast<float*>(sbins), mode == 0 && i == ns - 1);
+    }
+    if (FAMILY == 0 && P.item_contacts && mode == 0) {  // this lane's 4 cubes: contact points of the last sub-step
+      __syncwarp();
+      const int* itouch = reinterpret_cast<const int*>(reinterpret_cast<float*>(sbins) + HRL_EPW * 32) + es * 16;
+#pragma unroll
+      for (int i = 0; i < 4; i++) touch[i] = itouch[4 * k + i];
+      __syncwarp();
     }
     if (st.stats) {  // warp-uniform: inactive tail lanes contribute zeros (never guard a *_sync by `active`)
       const int na = __popc(__ballot_sync(HRL_FULL_MASK, active && k == 0));
@@ -336,6 +347,12 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
           }
         }
       }
+      const bool touch_pickup = first && todo == 1 && !(cfg.robot_coll_dist > 0.f);
+      if (touch_pickup) {  // ant_gather_env.py:113-116: one reward_collision per contact POINT of the robot with a cube
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          if (4 * k + i < cfg.n_food + cfg.n_poison) food_rew += (float)touch[i] * ((4 * k + i < cfg.n_food) ? 1.f : -1.f);
+      }
       food_rew = gsum(food_rew);
       const int nb = cfg.n_bins;
       if (commit) {
@@ -395,6 +412,15 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
           }
         }
         __syncwarp();
+      }
+      if (touch_pickup) {  // the cube moves AFTER the observation of this step was built (:96 before :113)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int gi = 4 * k + i;
+          if (gi >= cfg.n_food + cfg.n_poison || touch[i] == 0) continue;
+          if (cfg.respawn) place_item(cfg, genv, STREAM_ITEM, (uint32_t)T.steps_total, gi, s.O.x, s.O.y, it_x[i], it_y[i]);
+          else { it_x[i] = 100.f; it_y[i] = 0.f; }
+        }
       }
       fin = isfinite(o_z) && isfinite(o_v0) && isfinite(o_v1) && isfinite(o_v2) && isfinite(o_r) && isfinite(o_p) &&
             isfinite(rel1) && isfinite(sp1) && isfinite(rel2) && isfinite(sp2);
@@ -888,9 +914,12 @@ int hrl_default_config(int32_t kind, int32_t num_envs, hrl_config* c) {
   // non-default kwargs: off unless asked for
   c->sense_target = 0; c->maze_max_steps = -1; c->targ_dist_rew = 0;
   c->flag_use_sensor = 0; c->flag_switch_on_collision = 1; c->flag_max_target_dist = 0.f;
+  c->item_contacts = 0; c->item_friction = 1.5f * 0.5f; c->item_half = 0.125f; c->item_z = 0.1f;  // assets/food.xml:17-22
   switch (kind) {
     case HRL_ANT_GATHER:
-      c->world_size[0] = c->world_size[1] = 15; c->start_pos[2] = 0.75f; break;
+      c->world_size[0] = c->world_size[1] = 15; c->start_pos[2] = 0.75f;
+      c->item_contacts = 1;  // the food / poison cubes are real static colliders in the reference (gather_scene.py:66)
+      break;
     case HRL_POINT_GATHER:  // point_gather_env.py:8-21, point_bot.py:12,29, player_cube.xml:8
       c->world_size[0] = c->world_size[1] = 15; c->start_pos[2] = 0.5f; c->n_bins = 5;
       c->friction = 0.1f * 0.8f; c->torque_scale = 500.f; break;
@@ -964,6 +993,10 @@ static int validate(const hrl_config* c) {
   if (c->substeps < 1 || c->solver_iters < 0) return set_err(HRL_E_INVALID, "bad substeps/solver_iters");
   if (c->n_targets > HRL_MAX_TARGETS || c->flag_max_targets > 127) return set_err(HRL_E_INVALID, "too many targets");
   if (c->env_kind == HRL_POINT_GATHER && !c->use_sensor) return set_err(HRL_E_INVALID, "PointGather use_sensor=False is not built");
+  if (c->env_kind == HRL_POINT_GATHER && (c->item_contacts || !(c->robot_coll_dist > 0.f)))
+    return set_err(HRL_E_INVALID, "PointGather cube colliders / contact-based pickup are not built");
+  if (c->env_kind == HRL_ANT_GATHER && !(c->robot_coll_dist > 0.f) && !c->item_contacts)
+    return set_err(HRL_E_INVALID, "robot_coll_dist <= 0 (contact-based pickup) needs item_contacts = 1");
   if (c->env_kind == HRL_ANT_FLAGRUN && c->flag_max_targets < 1 && !(c->flag_max_target_dist > 0.f))
     return set_err(HRL_E_INVALID, "flagrun needs max_targets > 0 or max_target_dist > 0 (ant_flagrun_env.py:17-18)");
   if (c->env_kind == HRL_ANT_FLAGRUN && c->flag_use_sensor && c->n_bins < 2) return set_err(HRL_E_INVALID, "flagrun sensor needs >= 2 bins");

@@ -129,6 +129,14 @@ typedef struct hrl_config {
   int32_t flag_use_sensor;   /* ant_flagrun_env.py:15,122-130: wall lidar appended (n_bins, sensor_span, sensor_range) */
   int32_t flag_switch_on_collision; /* ant_flagrun_env.py:16,187-194, default 1                               */
   float flag_max_target_dist;/* ant_flagrun_env.py:14,80-89: create_close_target when flag_max_targets <= 0   */
+  /* food / poison cubes as colliders (assets/food.xml:17-22, gather_scene.py:62,66): static 0.25^3 boxes at z = 0.1.
+   * On by default for AntGather, like the reference; required by the contact-based pickup (robot_coll_dist <= 0,
+   * ant_gather_env.py:113-116).  With the distance-based pickup a cube is respawned once the torso is within 1 m,
+   * so leg-vs-cube contacts are rare (the candidate mask is almost always empty: < 0.5 % of the step time). */
+  int32_t item_contacts;
+  float item_friction;       /* 1.5 (ant.xml:9) x 0.5 (Bullet default of the cube URDF) [3P-MEM]               */
+  float item_half;           /* 0.125                                                                         */
+  float item_z;              /* 0.1 (gather_scene.py:62)                                                      */
 } hrl_config;
 
 typedef struct hrl_handle hrl_handle;

@@ -452,7 +452,7 @@ static void impulse_response(const hrlo_env* E, const kin_t* K, const real f[NDO
 /* ======================================================================================
  * contacts: sphere vs ground slab top / 4 wall inner faces / maze box
  * ====================================================================================== */
-typedef struct { int sphere; v3 n, P; real dist; } contact_t;
+typedef struct { int sphere; v3 n, P; real dist; real mu; int item; } contact_t;
 #define MAX_CONTACT_PER_GROUP 4
 #define MAX_CONTACTS 16
 
@@ -498,7 +498,10 @@ static int sphere_vs_box(v3 c, real r, const float lo[3], const float hi[3], v3*
   return 1;
 }
 
-static int detect_contacts(const hrlo_env* E, const kin_t* K, contact_t* C, int feet_ground[4]) {
+/* `touched` (optional, [HRL_MAX_ITEMS]): contact points per food/poison cube, what
+ * getContactPoints(robot) reports after the step (ant_gather_env.py:114) */
+static int detect_contacts(const hrlo_env* E, const env_state* s, const kin_t* K, contact_t* C, int feet_ground[4],
+                           int* touched) {
   const hrl_config* cfg = &E->cfg;
   const ant_model* M = &E->model;
   int n = 0, per_group[4] = {0, 0, 0, 0};
@@ -524,7 +527,26 @@ static int detect_contacts(const hrlo_env* E, const kin_t* K, contact_t* C, int 
       if (per_group[S->group] >= MAX_CONTACT_PER_GROUP) continue;
       per_group[S->group]++;
       C[n].sphere = si; C[n].n = nrm; C[n].dist = dist; C[n].P = vsub(c, vscale(nrm, r));
+      C[n].mu = (real)cfg->friction; C[n].item = -1;
       n++;
+    }
+    if (cfg->item_contacts) { /* food / poison cubes: static axis-aligned boxes (assets/food.xml, gather_scene.py:62) */
+      real hh = (real)cfg->item_half, reach = hh + r + margin;
+      for (int i = 0; i < cfg->n_food + cfg->n_poison; i++) {
+        real dx = c.v[0] - s->items[i][0], dy = c.v[1] - s->items[i][1];
+        if (R_FABS(dx) > reach || R_FABS(dy) > reach) continue;
+        float lo[3] = {(float)s->items[i][0] - cfg->item_half, (float)s->items[i][1] - cfg->item_half, cfg->item_z - cfg->item_half};
+        float hi[3] = {(float)s->items[i][0] + cfg->item_half, (float)s->items[i][1] + cfg->item_half, cfg->item_z + cfg->item_half};
+        v3 nrm; real dist;
+        sphere_vs_box(c, r, lo, hi, &nrm, &dist);
+        if (!(dist < margin)) continue;
+        if (touched) touched[i]++;
+        if (per_group[S->group] >= MAX_CONTACT_PER_GROUP) continue;
+        per_group[S->group]++;
+        C[n].sphere = si; C[n].n = nrm; C[n].dist = dist; C[n].P = vsub(c, vscale(nrm, r));
+        C[n].mu = (real)cfg->item_friction; C[n].item = i;
+        n++;
+      }
     }
   }
   return n;
@@ -600,14 +622,14 @@ static void integrate_pose(env_state* s, const real u[NDOF], real h) {
 
 /* one Bullet internal step of h = dt/substeps for the ant.  feet_ground = foot-vs-floor
  * manifold exists at the START of this sub-step (collision detection precedes dynamics). */
-static int ant_substep(hrlo_env* E, env_state* s, const real tau[8], int feet_ground[4]) {
+static int ant_substep(hrlo_env* E, env_state* s, const real tau[8], int feet_ground[4], int* touched) {
   const hrl_config* cfg = &E->cfg;
   const ant_model* M = &E->model;
   real h = (real)cfg->dt / (real)cfg->substeps;
   kin_t K;
   forward_kinematics(M, s, &K);
   contact_t C[MAX_CONTACTS];
-  int nc = detect_contacts(E, &K, C, feet_ground);
+  int nc = detect_contacts(E, s, &K, C, feet_ground, touched);
   real u[NDOF], udot[NDOF];
   for (int i = 0; i < 3; i++) { u[i] = s->ang[i]; u[3 + i] = s->vel[i]; }
   for (int j = 0; j < 8; j++) u[6 + j] = s->qd[j];
@@ -646,7 +668,6 @@ static int ant_substep(hrlo_env* E, env_state* s, const real tau[8], int feet_gr
 
   real dv[NDOF];
   for (int i = 0; i < NDOF; i++) dv[i] = 0;
-  real mu = (real)cfg->friction;
   for (int it = 0; it < cfg->solver_iters; it++) {
     for (int jj = 0; jj < nl; jj++) {
       int j = (it & 1) ? jj : nl - 1 - jj; /* Bullet alternates the non-contact row order */
@@ -666,7 +687,7 @@ static int ant_substep(hrlo_env* E, env_state* s, const real tau[8], int feet_gr
       if (!(tot > 0)) continue;
       row_t *a = &fr[2 * c], *b = &fr[2 * c + 1];
       real da = row_delta(a, dv), db = row_delta(b, dv);
-      real sa = a->lam + da, sb = b->lam + db, lim2 = mu * tot;
+      real sa = a->lam + da, sb = b->lam + db, lim2 = C[c].mu * tot;
       real len2 = sa * sa + sb * sb;
       if (len2 > lim2 * lim2) { real sc = lim2 / R_SQRT(len2); sa *= sc; sb *= sc; }
       da = sa - a->lam; db = sb - b->lam;
@@ -1012,7 +1033,8 @@ static void food_obs(const hrl_config* cfg, const env_state* s, real yaw, real* 
 /* Gather task layer after physics: ant_gather_env.py:84-119 / gather_base.py:80-109.
  * `base` = robot obs (ant: 26 = state[0], state[3:]; point: 8).  replay != NULL replays uniforms. */
 static void gather_task(hrlo_env* E, int e, env_state* s, const real* base, int nbase, real z_for_alive, int can_die,
-                        real yaw, const double* replay, int* replay_used, real* obs, real* rew, int* done, real* info) {
+                        real yaw, const double* replay, int* replay_used, const int* touched, real* obs, real* rew, int* done,
+                        real* info) {
   const hrl_config* cfg = &E->cfg;
   int n = cfg->n_food + cfg->n_poison;
   real food_rew = 0;
@@ -1039,6 +1061,22 @@ static void gather_task(hrlo_env* E, int e, env_state* s, const real* base, int 
   int alive = can_die ? (z_for_alive > (real)0.26) : 1; /* Ant.alive_bonus; point_bot.py:73-74 */
   *done = !alive;
   if (!all_finite(obs, nbase + food_obs_dim(cfg))) *done = 1; /* :101-103 */
+  if (!(cfg->robot_coll_dist > 0) && touched) {
+    /* ant_gather_env.py:113-116: AFTER the observation is built, one reward_collision per contact POINT of the
+     * robot with a cube (a cube touched by two spheres pays twice; it is respawned / parked once) */
+    for (int i = 0; i < n; i++) {
+      if (!touched[i]) continue;
+      food_rew += (real)touched[i] * ((i < cfg->n_food) ? 1 : -1);
+      if (cfg->respawn) {
+        real o[2];
+        int k = random_on_plane(cfg, s->pos[0], s->pos[1], cfg->seed, (uint32_t)(cfg->env_index_offset + e),
+                                STREAM_ITEM, (uint32_t)s->steps_total, i, replay ? replay + used : NULL, o);
+        used += 2 * k;
+        s->items[i][0] = o[0]; s->items[i][1] = o[1];
+      } else { s->items[i][0] = 100; s->items[i][1] = 0; }
+    }
+    if (replay_used) *replay_used = used;
+  }
   real dead_rew = alive ? 0 : (real)cfg->dying_cost;
   *rew = food_rew + dead_rew;
   info[0] = food_rew; info[1] = dead_rew;
@@ -1302,7 +1340,7 @@ static int step_env(hrlo_env* E, int e, const float* act, real* obs, real* rew, 
     for (int k = 0; k < cfg->substeps; k++) point_substep(E, s, (k == 0 || !cfg->torque_first_substep_only) ? f : z3);
     real base[8];
     point_base_obs(s, base);
-    gather_task(E, e, s, base, 8, 1, 0, 0, NULL, NULL, obs, rew, &done, info);
+    gather_task(E, e, s, base, 8, 1, 0, 0, NULL, NULL, NULL, obs, rew, &done, info);
   } else {
     real a[8], tau[8], zero[8] = {0};
     for (int j = 0; j < 8; j++) {
@@ -1311,8 +1349,10 @@ static int step_env(hrlo_env* E, int e, const float* act, real* obs, real* rew, 
       tau[j] = (real)cfg->torque_scale * a[j];
     }
     int feet_ground[4] = {0, 0, 0, 0};
-    for (int k = 0; k < cfg->substeps; k++)
-      if (ant_substep(E, s, (k == 0 || !cfg->torque_first_substep_only) ? tau : zero, feet_ground)) { done = 1; break; }
+    int touched[HRL_MAX_ITEMS] = {0};
+    for (int k = 0; k < cfg->substeps; k++) /* contact points as of the LAST internal step are what getContactPoints sees */
+      if (ant_substep(E, s, (k == 0 || !cfg->torque_first_substep_only) ? tau : zero, feet_ground,
+                      k == cfg->substeps - 1 ? touched : NULL)) { done = 1; break; }
     calc_t c;
     ant_calc_state(E, s, &c);
     s->wtd = c.wtd;
@@ -1321,7 +1361,7 @@ static int step_env(hrlo_env* E, int e, const float* act, real* obs, real* rew, 
       real base[26];
       base[0] = c.obs28[0];
       for (int i = 3; i < 28; i++) base[i - 2] = c.obs28[i];
-      gather_task(E, e, s, base, 26, z, 1, c.rpy[2], NULL, NULL, obs, rew, &done, info);
+      gather_task(E, e, s, base, 26, z, 1, c.rpy[2], NULL, NULL, touched, obs, rew, &done, info);
     } else {
       /* WalkerBaseBulletEnv.step [3P-MEM] SURVEY.md App. A.2 ; AntMjEnv.step envs/MjAnt.py:36-97 */
       int mj = (kind == HRL_ANT_MJ || kind == HRL_ANT_MAZE_MJ);
@@ -1385,9 +1425,12 @@ int hrlo_default_config(int32_t kind, int32_t num_envs, hrl_config* c) {
   c->electricity_cost = -2.0f; c->stall_torque_cost = -0.1f; c->joints_at_limit_cost = -0.1f;
   c->sense_target = 0; c->maze_max_steps = -1; c->targ_dist_rew = 0;
   c->flag_use_sensor = 0; c->flag_switch_on_collision = 1; c->flag_max_target_dist = 0.f;
+  c->item_contacts = 0; c->item_friction = 1.5f * 0.5f; c->item_half = 0.125f; c->item_z = 0.1f;
   switch (kind) {
     case HRL_ANT_GATHER:
-      c->world_size[0] = c->world_size[1] = 15; c->start_pos[2] = 0.75f; break;
+      c->world_size[0] = c->world_size[1] = 15; c->start_pos[2] = 0.75f;
+      c->item_contacts = 1; /* the food / poison cubes are real static colliders in the reference (gather_scene.py:66) */
+      break;
     case HRL_POINT_GATHER:
       c->world_size[0] = c->world_size[1] = 15; c->start_pos[2] = 0.5f; c->n_bins = 5;
       c->friction = 0.1f * 0.8f; c->torque_scale = 500.f; break;
@@ -1490,7 +1533,7 @@ int hrlo_substeps(hrlo_env* E, const float* actions, int n_sub) {
     } else {
       real tau[8], zero[8] = {0}; int fg[4];
       for (int j = 0; j < 8; j++) { real x = actions[e * A + j]; x = x > 1 ? 1 : (x < -1 ? -1 : x); tau[j] = (real)E->cfg.torque_scale * x; }
-      for (int k = 0; k < n_sub; k++) ant_substep(E, s, (k == 0 || !E->cfg.torque_first_substep_only) ? tau : zero, fg);
+      for (int k = 0; k < n_sub; k++) ant_substep(E, s, (k == 0 || !E->cfg.torque_first_substep_only) ? tau : zero, fg, NULL);
     }
   }
   return HRL_OK;
@@ -1544,7 +1587,7 @@ int hrlo_gather_task_replay(const hrl_config* cfg, const double* base, int nbase
   for (int i = 0; i < HRL_MAX_ITEMS; i++) { s->items[i][0] = (real)items_xy[2 * i]; s->items[i][1] = (real)items_xy[2 * i + 1]; }
   real b[32], o[64], rew, info[4]; int done;
   for (int i = 0; i < nbase; i++) b[i] = (real)base[i];
-  gather_task(E, 0, s, b, nbase, (real)xyz[2], can_die, (real)yaw, uniforms, used, o, &rew, &done, info);
+  gather_task(E, 0, s, b, nbase, (real)xyz[2], can_die, (real)yaw, uniforms, used, NULL, o, &rew, &done, info);
   for (int i = 0; i < nbase + food_obs_dim(&c); i++) obs[i] = o[i];
   for (int i = 0; i < HRL_MAX_ITEMS; i++) { items_xy[2 * i] = s->items[i][0]; items_xy[2 * i + 1] = s->items[i][1]; }
   rew_done_info[0] = rew; rew_done_info[1] = done; rew_done_info[2] = info[0]; rew_done_info[3] = info[1];

@@ -67,11 +67,14 @@ def test_kwargs_mapping():
         K.apply_kwargs(cfg, K.HRL_ANT_GATHER, dict(nonsense=1))
     K.apply_kwargs(cfg, K.HRL_ANT_GATHER, dict(use_sensor=False))      # get_abs_pos: xy of the nearest items
     assert cfg.use_sensor == 0 and K.obs_dim(cfg) == 26 + 2 * 3 + 2 * 2
-    with pytest.raises(NotImplementedError):                             # still outside the built scope: fail loudly
-        K.apply_kwargs(cfg, K.HRL_ANT_GATHER, dict(robot_coll_dist=0))
+    assert cfg.item_contacts == 1 and cfg.item_friction == pytest.approx(0.75)   # cubes are colliders by default
+    K.apply_kwargs(cfg, K.HRL_ANT_GATHER, dict(item_contacts=False, robot_coll_dist=0))   # contact-based pickup needs them
+    assert cfg.item_contacts == 1
     p = _cabi.default_config(K.HRL_POINT_GATHER, 1)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):                             # still outside the built scope: fail loudly
         K.apply_kwargs(p, K.HRL_POINT_GATHER, dict(use_sensor=False))
+    with pytest.raises(NotImplementedError):
+        K.apply_kwargs(_cabi.default_config(K.HRL_POINT_GATHER, 1), K.HRL_POINT_GATHER, dict(robot_coll_dist=0))
     f = _cabi.default_config(K.HRL_ANT_FLAGRUN, 1)
     K.apply_kwargs(f, K.HRL_ANT_FLAGRUN, dict(use_sensor=True, sensor_bins=6, switch_flag_on_collision=False))
     assert f.flag_use_sensor == 1 and f.flag_switch_on_collision == 0 and K.obs_dim(f) == 34

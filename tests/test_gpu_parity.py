@@ -329,6 +329,8 @@ KWARG_CASES = [
     ("AntMazeBulletEnv-v0", dict(sense_target=True)),                       # ant_maze_bullet_env.py:135-178
     ("AntMazeBulletEnv-v0", dict(max_steps=20, done_at_target=False, targ_dist_rew=True, inner_rew_weight=0.3)),
     ("AntMazeBulletEnv-v0", dict(target_encoding=1, sense_walls=False, tol=3.0)),
+    ("AntGatherBulletEnv-v0", dict(robot_coll_dist=0)),                     # contact-based pickup, ant_gather_env.py:113-116
+    ("AntGatherBulletEnv-v0", dict(item_contacts=False)),                   # cube colliders off (they are on by default)
     ("AntFlagrunBulletEnv-v0", dict(use_sensor=True)),                      # ant_flagrun_env.py:122-130
     ("AntFlagrunBulletEnv-v0", dict(switch_flag_on_collision=False, timeout=15, max_targets=3, tolerance=2.5)),
     ("AntFlagrunBulletEnv-v0", dict(max_targets=0, max_target_dist=4.0, tolerance=1.5, timeout=10)),  # create_close_target :80-89
@@ -371,3 +373,48 @@ def test_kwargs_one_step_parity(env_id, kw):
         np.testing.assert_allclose(f2.cpu().numpy()[fin][:, K.SF_TARGET:K.SF_TARGET + 2], fo[fin][:, K.SF_TARGET:K.SF_TARGET + 2], atol=1e-4)
     assert checked > 0.5 * N * T or "max_steps" in kw
     assert n_out <= 5e-3 * max(checked, 1) + 2, (n_out, checked)
+
+
+@pytest.mark.parametrize("kw", [dict(robot_coll_dist=0), dict(robot_coll_dist=0, respawn=False), dict(robot_coll_dist=0.04)],
+                         ids=["touch", "touch-norespawn", "colliders-only"])
+def test_cube_colliders_and_contact_pickup(kw):
+    """Food / poison cubes as colliders (assets/food.xml, gather_scene.py:62-66) and the contact-based pickup
+    (ant_gather_env.py:113-116).  Random actions never reach a cube, so the cubes are put where the feet are:
+    settle the ants, then place the 16 items on a ring around each torso and step CUDA and the oracle from
+    the same states."""
+    N = 256
+    g, o = _envs("AntGatherBulletEnv-v0", N, seed=4, **kw)
+    g.reset(); o.reset()
+    gen = torch.Generator().manual_seed(9)
+    for t in range(30):
+        g.step((torch.rand(N, 8, generator=gen) * 2 - 1).cuda())
+    f, i = g.get_state()
+    f = f.cpu().numpy()
+    rng = np.random.default_rng(2)
+    ang = rng.uniform(0, 2 * np.pi, (N, 16)); rad = rng.uniform(0.45, 1.05, (N, 16))
+    f[:, K.SF_ITEMS:K.SF_ITEMS + 32:2] = f[:, [K.SF_POS]] + rad * np.cos(ang)
+    f[:, K.SF_ITEMS + 1:K.SF_ITEMS + 32:2] = f[:, [K.SF_POS + 1]] + rad * np.sin(ang)
+    g.set_state(torch.tensor(f), i)
+    events = contacts = checked = n_out = 0
+    for t in range(12):
+        a = torch.rand(N, 8, generator=gen) * 2 - 1
+        f, i = g.get_state()
+        o.set_state(f.cpu().numpy().astype(np.float64), i.cpu().numpy())
+        og, rg, dg, info = g.step(a.cuda())
+        oo, ro, do, io = o.step(a.numpy())
+        f2, i2 = g.get_state(); fo, io2 = o.get_state()
+        dg = dg.cpu().numpy(); rg = rg.cpu().numpy()
+        live = (dg == do) & ~dg
+        ep, ev = _state_err(f2.cpu().numpy()[live], fo[live])
+        ok = (ep < POS_TOL) & (ev < VEL_TOL)
+        idx = np.nonzero(live)[0][ok]
+        n_out += int((~ok).sum()) + int((dg != do).sum()); checked += int(live.sum())
+        assert np.abs(rg[idx] - ro[idx]).max(initial=0) <= REW_TOL           # same cubes touched, same number of contact points
+        items_g = f2.cpu().numpy()[idx][:, K.SF_ITEMS:K.SF_ITEMS + 32]; items_o = fo[idx][:, K.SF_ITEMS:K.SF_ITEMS + 32]
+        np.testing.assert_allclose(items_g, items_o, atol=1e-5)              # respawned / parked identically
+        events += int((np.abs(info["food_rew"].cpu().numpy()) > 0).sum())
+        contacts = o.stats()["contacts_per_substep"]
+    assert n_out <= 0.02 * checked, (n_out, checked)   # more knife-edge contacts than on flat ground: box edges
+    if not (kw.get("robot_coll_dist", 1) > 0):
+        assert events > 20, events                     # the feet do touch cubes in this set-up
+    print("cube test", kw, "pickup events", events, "contacts/substep", contacts, "outliers", n_out, "/", checked)
