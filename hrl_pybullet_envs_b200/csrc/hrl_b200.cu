@@ -632,32 +632,37 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
 }
 
 // ------------------------------------------------------------------------------------------
-// PointGather: one thread per env (point_bot.py, gather_base.py:74-109).  The cube only
-// translates (north star: "the PointGather point-mass integrator"); state lives in the same
-// DevState arrays (base rows 0/2, items).
+// PointGather (point_bot.py, gather_base.py:74-109): 16 lanes per env, lane j owns item j.  The cube
+// only translates (north star: "the PointGather point-mass integrator"); its trivial physics is
+// evaluated redundantly by the 16 lanes, the per-item work (pickup, respawn, sector bin) is parallel.
+// State lives in the same DevState arrays (base rows 0/2, items).
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sum16(float v) {
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) v += __shfl_xor_sync(HRL_FULL_MASK, v, o);
+  return v;
+}
+
+// One internal step.  Candidate contacts are the 5 fixed surfaces (ground, walls +x -x +y -y) in that order;
+// everything is indexed statically so that the solver state stays in registers.
 __device__ __forceinline__ void point_substep(V3& pos, V3& vel, V3 force, const SubstepParams& P) {
-  const float m = pointbot::MASS, half = pointbot::HALF;
+  const float m = pointbot::MASS, half = pointbot::HALF, im = 1.0f / m;
   const float wx = P.wx - half, wy = P.wy - half;
-  V3 Nn[5]; float Dd[5]; int nc = 0;
-  const float dg = pos.z - half - P.gz;
-  if (dg < P.margin) { Nn[nc] = mk(0.f, 0.f, 1.f); Dd[nc++] = dg; }
-  if (P.has_walls) {
-    if (wx - pos.x < P.margin) { Nn[nc] = mk(-1.f, 0.f, 0.f); Dd[nc++] = wx - pos.x; }
-    if (pos.x + wx < P.margin) { Nn[nc] = mk(1.f, 0.f, 0.f); Dd[nc++] = pos.x + wx; }
-    if (wy - pos.y < P.margin) { Nn[nc] = mk(0.f, -1.f, 0.f); Dd[nc++] = wy - pos.y; }
-    if (pos.y + wy < P.margin) { Nn[nc] = mk(0.f, 1.f, 0.f); Dd[nc++] = pos.y + wy; }
-  }
-  V3 f = mk(force.x, force.y, force.z - m * P.g) + (-m * (P.kl + P.kl * norm(vel))) * vel;
-  V3 v = vel + (P.h / m) * f;
+  const V3 Nn[5] = {mk(0.f, 0.f, 1.f), mk(-1.f, 0.f, 0.f), mk(1.f, 0.f, 0.f), mk(0.f, -1.f, 0.f), mk(0.f, 1.f, 0.f)};
+  const float Dd[5] = {pos.z - half - P.gz, wx - pos.x, pos.x + wx, wy - pos.y, pos.y + wy};
+  bool on[5];
+#pragma unroll
+  for (int c = 0; c < 5; c++) on[c] = (c == 0 || P.has_walls) && (Dd[c] < P.margin);
+  const V3 f = mk(force.x, force.y, force.z - m * P.g) + (-m * (P.kl + P.kl * norm(vel))) * vel;
+  V3 v = vel + (P.h * im) * f;
   v = mk(clampf(v.x, P.vmax), clampf(v.y, P.vmax), clampf(v.z, P.vmax));
   float lamn[5], lama[5], lamb[5], rhsn[5], rhsa[5], rhsb[5];
   V3 T1[5], T2[5];
-  const float inv_h = 1.0f / P.h;
-  for (int c = 0; c < nc; c++) {
+#pragma unroll
+  for (int c = 0; c < 5; c++) {
     const float rel = dot(Nn[c], v);
     float posErr = 0.f, velErr = -rel;
-    if (Dd[c] > 0.f) velErr -= Dd[c] * inv_h; else posErr = -Dd[c] * P.erp_c * inv_h;
+    if (Dd[c] > 0.f) velErr -= Dd[c] * P.inv_h; else posErr = -Dd[c] * P.erp_c * P.inv_h;
     rhsn[c] = (posErr + velErr) * m;
     plane_space(Nn[c], T1[c], T2[c]);
     rhsa[c] = -dot(T1[c], v) * m; rhsb[c] = -dot(T2[c], v) * m;
@@ -665,44 +670,48 @@ __device__ __forceinline__ void point_substep(V3& pos, V3& vel, V3 force, const 
   }
   V3 dv = mk(0.f, 0.f, 0.f);
   for (int it = 0; it < P.iters; it++) {
-    for (int c = 0; c < nc; c++) {
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+      if (!on[c]) continue;
       float dl = rhsn[c] - dot(Nn[c], dv) * m;
       if (lamn[c] + dl < 0.f) dl = -lamn[c];
-      lamn[c] += dl; dv = dv + (dl / m) * Nn[c];
+      lamn[c] += dl; dv = dv + (dl * im) * Nn[c];
     }
-    for (int c = 0; c < nc; c++) {
-      if (!(lamn[c] > 0.f)) continue;
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+      if (!on[c] || !(lamn[c] > 0.f)) continue;
       float sa = lama[c] + rhsa[c] - dot(T1[c], dv) * m, sb = lamb[c] + rhsb[c] - dot(T2[c], dv) * m;
       const float lim = P.mu * lamn[c], len2 = sa * sa + sb * sb;
       if (len2 > lim * lim) { const float sc = lim * rsqrtf(len2); sa *= sc; sb *= sc; }
       const float da = sa - lama[c], db = sb - lamb[c];
       lama[c] = sa; lamb[c] = sb;
-      dv = dv + (da / m) * T1[c] + (db / m) * T2[c];
+      dv = dv + (da * im) * T1[c] + (db * im) * T2[c];
     }
   }
   vel = v + dv;
   pos = pos + P.h * vel;
 }
 
-__global__ void __launch_bounds__(128)
+#define HRL_POINT_EPB 8  // envs per 128-thread block
+__global__ void __launch_bounds__(16 * HRL_POINT_EPB)
 point_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float* __restrict__ actions,
                  const uint8_t* __restrict__ mask, float* __restrict__ obs_out, float* __restrict__ rew_out,
                  uint8_t* __restrict__ done_out, float* __restrict__ info_out, float* __restrict__ term_out, int mode,
                  int n_sub, int D) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= cfg.num_envs) return;
+  __shared__ unsigned long long sb[HRL_POINT_EPB][2][HRL_MAX_BINS];
+  __shared__ float sobs[HRL_POINT_EPB][8 + 2 * HRL_MAX_BINS];
+  const int j = threadIdx.x & 15, eb = threadIdx.x >> 4;
+  const int e_raw = blockIdx.x * HRL_POINT_EPB + eb;
+  const bool valid = e_raw < cfg.num_envs;
+  const int e = valid ? e_raw : cfg.num_envs - 1;  // tail lanes shadow the last env (no stores): every *_sync stays warp-wide
   const uint32_t genv = (uint32_t)(cfg.env_index_offset + e);
-  float4 b0 = st.base[e * 4 + 0], b2 = st.base[e * 4 + 2];
+  const float4 b0 = st.base[e * 4 + 0], b2 = st.base[e * 4 + 2];
   int4 i0 = st.misci[e * 2 + 0];
   V3 pos = mk(b0.x, b0.y, b0.z), vel = mk(b2.x, b2.y, b2.z);
   float initial_z = b0.w;
-  float ix[16], iy[16];
-#pragma unroll
-  for (int l = 0; l < 8; l++) {
-    const float4 a = st.items[e * 8 + l];
-    ix[2 * l] = a.x; iy[2 * l] = a.y; ix[2 * l + 1] = a.z; iy[2 * l + 1] = a.w;
-  }
   const int n_items = cfg.n_food + cfg.n_poison, nb = cfg.n_bins;
+  const bool has_item = j < n_items;
+  float2 it = reinterpret_cast<const float2*>(st.items)[e * 16 + j];  // item j: food 0..n_food-1, then poison
   if (mode <= 1) {
     // point_bot.py:28-31: F = a/|a| * 500 N in the world frame (NaN for a == 0: kept, see gather_base.py:99-101)
     const float ax = actions[e * 2], ay = actions[e * 2 + 1], nn = sqrtf(ax * ax + ay * ay);
@@ -711,73 +720,88 @@ point_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const floa
     const int ns = mode == 0 ? cfg.substeps : n_sub;
     for (int i = 0; i < ns; i++) point_substep(pos, vel, (i == 0 || !cfg.torque_first_substep_only) ? F : Z, P);
   }
-  bool do_reset = false, emit = (mode != 1);
-  if (mode == 2) { do_reset = mask ? mask[e] != 0 : true; emit = do_reset; }
-  float food_rew = 0.f;
-  int done = 0;
+  bool do_reset = (mode == 2) && (mask ? mask[e] != 0 : true);
+  bool work = (mode == 0) || (mode == 3) || do_reset;  // this env still has an observation to produce
+  bool stepping = (mode == 0);
   for (int pass = 0; pass < 2; pass++) {
-    if (do_reset) {
+    if (!__any_sync(HRL_FULL_MASK, work)) break;
+    if (work && do_reset) {
       i0.x = 0;
       pos = mk(cfg.start_pos[0], cfg.start_pos[1], cfg.start_pos[2]); vel = mk(0.f, 0.f, 0.f);  // point_bot.py:12,25-26
       initial_z = 1.f;                                                                            // point_bot.py:18
-      for (int gi = 0; gi < n_items; gi++) place_item(cfg, genv, STREAM_ITEM_RESET, (uint32_t)i0.y, gi, 0.f, 0.f, ix[gi], iy[gi]);
+      if (has_item) place_item(cfg, genv, STREAM_ITEM_RESET, (uint32_t)i0.y, j, 0.f, 0.f, it.x, it.y);
       i0.y++;
       do_reset = false;
     }
-    if (mode == 0 && pass == 0) {
-      for (int gi = 0; gi < n_items; gi++) {
-        const double dx = __dsub_rn((double)ix[gi], (double)pos.x), dy = __dsub_rn((double)iy[gi], (double)pos.y);
-        const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-        if (d2 < (double)cfg.robot_coll_dist) {
-          food_rew += (gi < cfg.n_food) ? 1.f : -1.f;
-          if (cfg.respawn) place_item(cfg, genv, STREAM_ITEM, (uint32_t)i0.z, gi, pos.x, pos.y, ix[gi], iy[gi]);
-          else { ix[gi] = 100.f; iy[gi] = 0.f; }
-        }
+    float rew_j = 0.f;
+    if (work && stepping && has_item) {  // pickup of this lane's item (gather_base.py:84-90, gather_scene.py:95-114)
+      const double dx = __dsub_rn((double)it.x, (double)pos.x), dy = __dsub_rn((double)it.y, (double)pos.y);
+      const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+      if (d2 < (double)cfg.robot_coll_dist) {
+        rew_j = (j < cfg.n_food) ? 1.f : -1.f;
+        if (cfg.respawn) place_item(cfg, genv, STREAM_ITEM, (uint32_t)i0.z, j, pos.x, pos.y, it.x, it.y);
+        else { it.x = 100.f; it.y = 0.f; }
       }
     }
-    // observation: point_bot.py:48-67 (roll = pitch = yaw = 0) + sensor gather_base.py:118-168
-    float o[8 + 2 * HRL_MAX_BINS];
-    {
-      float sa, ca;
-      sincosf(atan2f(0.f - pos.y, 0.f - pos.x), &sa, &ca);
-      o[0] = pos.z - initial_z; o[1] = sa; o[2] = ca; o[3] = 0.3f * vel.x; o[4] = 0.3f * vel.y; o[5] = 0.3f * vel.z; o[6] = 0.f; o[7] = 0.f;
-      double best[2 * HRL_MAX_BINS];
-      for (int b = 0; b < 2 * nb; b++) best[b] = -1.0;
-      for (int gi = 0; gi < n_items; gi++) {
-        double d2;
-        const int b = gather_item_bin(pos.x, pos.y, 0.f, ix[gi], iy[gi], nb, cfg.sensor_range, cfg.sensor_span, &d2);
-        if (b >= 0) {
-          const int idx = (gi < cfg.n_food ? 0 : nb) + b;
-          if (best[idx] < 0.0 || d2 < best[idx]) best[idx] = d2;
-        }
-      }
-      for (int b = 0; b < 2 * nb; b++) o[8 + b] = best[b] < 0.0 ? 0.f : (float)(1.0 - best[b] / (double)cfg.sensor_range);
+    const float food_rew = sum16(rew_j);
+    // observation: point_bot.py:48-67 (roll = pitch = yaw = 0) + sector sensor gather_base.py:118-168
+    for (int b = j; b < 2 * HRL_MAX_BINS; b += 16) sb[eb][b / HRL_MAX_BINS][b % HRL_MAX_BINS] = 0x7ff0000000000000ull;
+    __syncwarp();
+    if (work && has_item) {
+      double d2;
+      const int b = gather_item_bin(pos.x, pos.y, 0.f, it.x, it.y, nb, cfg.sensor_range, cfg.sensor_span, &d2);
+      if (b >= 0) atomicMin(&sb[eb][j < cfg.n_food ? 0 : 1][b], (unsigned long long)__double_as_longlong(d2));
     }
-    if (mode == 0 && pass == 0) {
+    __syncwarp();
+    float sa, ca;
+    sincosf(atan2f(0.f - pos.y, 0.f - pos.x), &sa, &ca);
+    const float o8[8] = {pos.z - initial_z, sa, ca, 0.3f * vel.x, 0.3f * vel.y, 0.3f * vel.z, 0.f, 0.f};
+    if (j < 8) {
+      float v = o8[0];
+#pragma unroll
+      for (int q = 1; q < 8; q++) v = (j == q) ? o8[q] : v;
+      sobs[eb][j] = v;
+    }
+    for (int b = j; b < 2 * nb; b += 16) {
+      const int ty = b / nb, bb = b - ty * nb;
+      const unsigned long long bits = sb[eb][ty][bb];
+      sobs[eb][8 + b] = bits == 0x7ff0000000000000ull ? 0.f : (float)(1.0 - __longlong_as_double((long long)bits) / (double)cfg.sensor_range);
+    }
+    __syncwarp();
+    bool emit = work && (mode != 1);
+    bool again = false;
+    if (work && stepping) {
       bool fin = true;
-      for (int i = 0; i < 8; i++) fin = fin && isfinite(o[i]);
-      done = !fin;  // PointBot.alive_bonus is always 1 (point_bot.py:73-74)
+#pragma unroll
+      for (int q = 0; q < 8; q++) fin = fin && isfinite(o8[q]);
+      int done = !fin;  // PointBot.alive_bonus is always 1 (point_bot.py:73-74)
       i0.x++; i0.z++;
       float trunc = 0.f;
       if (cfg.max_episode_steps > 0 && i0.x >= cfg.max_episode_steps) { trunc = done ? 0.f : 1.f; done = 1; }
-      rew_out[e] = food_rew;
-      done_out[e] = (uint8_t)done;
-      if (info_out) reinterpret_cast<float4*>(info_out)[e] = make_float4(food_rew, 0.f, trunc, (float)i0.x);
-      if (done && cfg.auto_reset) {
-        if (term_out) for (int i = 0; i < D; i++) term_out[(size_t)e * D + i] = o[i];
-        do_reset = true;
-        continue;
+      if (valid && j == 0) {
+        rew_out[e] = food_rew;
+        done_out[e] = (uint8_t)done;
+        if (info_out) reinterpret_cast<float4*>(info_out)[e] = make_float4(food_rew, 0.f, trunc, (float)i0.x);
       }
+      if (done && cfg.auto_reset) {
+        if (term_out && valid) for (int q = j; q < D; q += 16) term_out[(size_t)e * D + q] = sobs[eb][q];
+        do_reset = true; again = true; emit = false;
+      }
+      stepping = false;
     }
-    if (emit && obs_out) for (int i = 0; i < D; i++) obs_out[(size_t)e * D + i] = o[i];
-    break;
+    if (emit && obs_out && valid) for (int q = j; q < D; q += 16) obs_out[(size_t)e * D + q] = sobs[eb][q];
+    work = again;
+    __syncwarp();
   }
-  st.base[e * 4 + 0] = make_float4(pos.x, pos.y, pos.z, initial_z);
-  st.base[e * 4 + 1] = make_float4(0.f, 0.f, 0.f, 1.f);  // the cube never rotates
-  st.base[e * 4 + 2] = make_float4(vel.x, vel.y, vel.z, 0.f);
-  st.misci[e * 2 + 0] = i0;
-#pragma unroll
-  for (int l = 0; l < 8; l++) st.items[e * 8 + l] = make_float4(ix[2 * l], iy[2 * l], ix[2 * l + 1], iy[2 * l + 1]);
+  if (valid) {
+    if (j == 0) {
+      st.base[e * 4 + 0] = make_float4(pos.x, pos.y, pos.z, initial_z);
+      st.base[e * 4 + 1] = make_float4(0.f, 0.f, 0.f, 1.f);  // the cube never rotates
+      st.base[e * 4 + 2] = make_float4(vel.x, vel.y, vel.z, 0.f);
+      st.misci[e * 2 + 0] = i0;
+    }
+    reinterpret_cast<float2*>(st.items)[e * 16 + j] = it;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1081,7 +1105,7 @@ static int launch_env(hrl_handle* h, int mode, int n_sub, const float* act, cons
     else cudaGetLastError();
   }
   if (h->cfg.env_kind == HRL_POINT_GATHER) {
-    const int B = 128, G = (h->N + B - 1) / B;
+    const int B = 16 * HRL_POINT_EPB, G = (h->N + HRL_POINT_EPB - 1) / HRL_POINT_EPB;
     point_env_kernel<<<G, B, 0, s>>>(h->cfg, h->st, act, mask, obs, rew, done, info, term, mode, n_sub, h->D);
   } else {
     const int T = 32 * HRL_WARPS_PER_CTA, EPC = HRL_EPW * HRL_WARPS_PER_CTA, G = (h->N + EPC - 1) / EPC;
