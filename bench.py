@@ -167,7 +167,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from hrl_pybullet_envs_b200 import VecEnv, _cabi, roofline
-    from hrl_pybullet_envs_b200.sharding import max_over_ranks, shard_offset, sum_episode_stats
+    from hrl_pybullet_envs_b200.sharding import max_over_ranks, shard_offset
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -242,8 +242,7 @@ def run_ours(args):
 
     dev_ms, b2b_ms, e2e_ms, e2e_copy_ms = max_over_ranks([dev_ms, b2b_ms, e2e_s * 1e3, e2e_modes["copy"] * 1e3], device=dev)
     # optional episode statistics over NVLink (the only other collective; not on the step path)
-    f, i = env.get_state()
-    episodes, env_steps = sum_episode_stats(i[:, 1].sum().item(), i[:, 2].sum().item(), device=dev)
+    ep_stats = env.episode_stats(aggregate=True)   # in-kernel accumulators, summed over ranks
 
     if rank == 0:
         hbm_peak, sm_max, which = peaks()
@@ -270,7 +269,7 @@ def run_ours(args):
                     "value_copy_mode": total_envs * args.steps / (e2e_copy_ms * 1e-3),
                     "copy_mode": "pinned H2D memcpy, kernel, ONE packed D2H memcpy, stream sync"},
             "gpu_launches": int(launches),
-            "episode_stats": {"episodes_started": episodes, "env_steps_total": env_steps},
+            "episode_stats": ep_stats,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": roofline.BYTES_PER_ENV_STEP * N / launch_s / 1e9, "peak": hbm_peak,
                          "unit": "GB/s", "frac": roofline.BYTES_PER_ENV_STEP * N / launch_s / 1e9 / hbm_peak,

@@ -22,6 +22,7 @@ HRL_STATE_I = 8
 # float-state offsets (enum HRL_SF_* in include/hrl_b200.h)
 SF_POS, SF_QUAT, SF_LINVEL, SF_ANGVEL, SF_Q, SF_QD = 0, 3, 7, 10, 13, 21
 SF_INITIAL_Z, SF_POTENTIAL, SF_TARGET, SF_WTD, SF_FEET, SF_ITEMS = 29, 30, 31, 33, 34, 38
+SF_RETURN, SF_RETURN_SUM = 70, 71
 SI_T, SI_EPISODE, SI_STEPS, SI_GOALS_LEFT, SI_SINCE, SI_REWARDED = range(6)
 
 

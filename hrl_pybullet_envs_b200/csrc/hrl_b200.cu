@@ -30,7 +30,7 @@ struct DevState {
   float4* base;   // [N][4]: (pos.xyz, initial_z) (quat xyzw) (vel.xyz, potential) (ang.xyz, wtd)
   float4* leg;    // [N][4 legs]: (q_hip, q_ankle, qd_hip, qd_ankle)
   float4* items;  // [N][4 lanes][2]: items 4k..4k+3 as (x0,y0,x1,y1)(x2,y2,x3,y3)
-  float4* miscf;  // [N][2]: (target.x, target.y, -, -) (feet0..3)
+  float4* miscf;  // [N][2]: (target.x, target.y, running return, sum of finished returns) (feet0..3)
   int4* misci;    // [N][2]: (t, episode, steps_total, goals_left) (since, rewarded, -, -)
   unsigned long long* stats;  // [4]: contacts, limit rows, env-substeps, non-finite resets
   // completion signal of the zero-copy host path: the last CTA to finish writes fin_seq to the
@@ -130,6 +130,7 @@ __device__ __noinline__ void place_item(const hrl_config& cfg, uint32_t genv, ui
 
 struct TaskRegs {  // replicated per-env task state held in registers
   float initial_z, potential, wtd, tx, ty;
+  float ret, ret_sum;  // episode-return accumulators (HRL_SF_RETURN, HRL_SF_RETURN_SUM)
   float feet[4];
   int t, episode, steps_total, goals_left, since, rewarded;
 };
@@ -191,7 +192,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
     s.v = mk(b2.x, b2.y, b2.z); T.potential = b2.w;
     s.w = mk(b3.x, b3.y, b3.z); T.wtd = b3.w;
     s.q1 = lg.x; s.q2 = lg.y; s.qd1 = lg.z; s.qd2 = lg.w;
-    T.tx = m0.x; T.ty = m0.y;
+    T.tx = m0.x; T.ty = m0.y; T.ret = m0.z; T.ret_sum = m0.w;
     T.feet[0] = m1.x; T.feet[1] = m1.y; T.feet[2] = m1.z; T.feet[3] = m1.w;
     T.t = i0.x; T.episode = i0.y; T.steps_total = i0.z; T.goals_left = i0.w; T.since = i1.x; T.rewarded = i1.y;
   }
@@ -256,7 +257,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
   for (int guard = 0; guard < 5; guard++) {
     // reset requests are executed first (register state only)
     if (todo == 3) {
-      T.t = 0;
+      T.t = 0; T.ret = 0.f;
       s.O = mk(cfg.start_pos[0], cfg.start_pos[1], cfg.start_pos[2]);
       s.qx = s.qy = s.qz = 0.f; s.qw = 1.f;
       s.v = mk(0.f, 0.f, 0.f); s.w = mk(0.f, 0.f, 0.f);
@@ -432,6 +433,8 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
         T.t++; T.steps_total++;
         float trunc = 0.f;
         if (cfg.max_episode_steps > 0 && T.t >= cfg.max_episode_steps) { trunc = done ? 0.f : 1.f; done = 1; }
+        T.ret += food_rew + dead_rew;
+        if (done) { T.ret_sum += T.ret; T.ret = 0.f; }
         if (active && k == 0) {
           rew_out[e] = food_rew + dead_rew;
           done_out[e] = (uint8_t)done;
@@ -549,6 +552,8 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
         T.t++; T.steps_total++;
         float trunc = 0.f;
         if (cfg.max_episode_steps > 0 && T.t >= cfg.max_episode_steps) { trunc = done ? 0.f : 1.f; done = 1; }
+        T.ret += rew;
+        if (done) { T.ret_sum += T.ret; T.ret = 0.f; }
         if (active && k == 0) {
           rew_out[e] = rew;
           done_out[e] = (uint8_t)done;
@@ -584,7 +589,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       st.base[e * 4 + 1] = make_float4(s.qx, s.qy, s.qz, s.qw);
       st.base[e * 4 + 2] = make_float4(s.v.x, s.v.y, s.v.z, T.potential);
       st.base[e * 4 + 3] = make_float4(s.w.x, s.w.y, s.w.z, T.wtd);
-      st.miscf[e * 2 + 0] = make_float4(T.tx, T.ty, 0.f, 0.f);
+      st.miscf[e * 2 + 0] = make_float4(T.tx, T.ty, T.ret, T.ret_sum);
       st.miscf[e * 2 + 1] = make_float4(T.feet[0], T.feet[1], T.feet[2], T.feet[3]);
       st.misci[e * 2 + 0] = make_int4(T.t, T.episode, T.steps_total, T.goals_left);
       st.misci[e * 2 + 1] = make_int4(T.since, T.rewarded, 0, 0);
@@ -706,6 +711,7 @@ point_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const floa
   const int e = valid ? e_raw : cfg.num_envs - 1;  // tail lanes shadow the last env (no stores): every *_sync stays warp-wide
   const uint32_t genv = (uint32_t)(cfg.env_index_offset + e);
   const float4 b0 = st.base[e * 4 + 0], b2 = st.base[e * 4 + 2];
+  float4 m0 = st.miscf[e * 2 + 0];  // .z running episode return, .w sum of finished returns
   int4 i0 = st.misci[e * 2 + 0];
   V3 pos = mk(b0.x, b0.y, b0.z), vel = mk(b2.x, b2.y, b2.z);
   float initial_z = b0.w;
@@ -726,7 +732,7 @@ point_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const floa
   for (int pass = 0; pass < 2; pass++) {
     if (!__any_sync(HRL_FULL_MASK, work)) break;
     if (work && do_reset) {
-      i0.x = 0;
+      i0.x = 0; m0.z = 0.f;
       pos = mk(cfg.start_pos[0], cfg.start_pos[1], cfg.start_pos[2]); vel = mk(0.f, 0.f, 0.f);  // point_bot.py:12,25-26
       initial_z = 1.f;                                                                            // point_bot.py:18
       if (has_item) place_item(cfg, genv, STREAM_ITEM_RESET, (uint32_t)i0.y, j, 0.f, 0.f, it.x, it.y);
@@ -778,6 +784,8 @@ point_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const floa
       i0.x++; i0.z++;
       float trunc = 0.f;
       if (cfg.max_episode_steps > 0 && i0.x >= cfg.max_episode_steps) { trunc = done ? 0.f : 1.f; done = 1; }
+      m0.z += food_rew;
+      if (done) { m0.w += m0.z; m0.z = 0.f; }
       if (valid && j == 0) {
         rew_out[e] = food_rew;
         done_out[e] = (uint8_t)done;
@@ -798,6 +806,7 @@ point_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const floa
       st.base[e * 4 + 0] = make_float4(pos.x, pos.y, pos.z, initial_z);
       st.base[e * 4 + 1] = make_float4(0.f, 0.f, 0.f, 1.f);  // the cube never rotates
       st.base[e * 4 + 2] = make_float4(vel.x, vel.y, vel.z, 0.f);
+      st.miscf[e * 2 + 0] = m0;
       st.misci[e * 2 + 0] = i0;
     }
     reinterpret_cast<float2*>(st.items)[e * 16 + j] = it;
@@ -822,7 +831,7 @@ __global__ void get_state_kernel(int N, DevState st, float* __restrict__ f, int3
     o[HRL_SF_Q + 2 * k] = l.x; o[HRL_SF_Q + 2 * k + 1] = l.y; o[HRL_SF_QD + 2 * k] = l.z; o[HRL_SF_QD + 2 * k + 1] = l.w;
   }
   const float4 m0 = st.miscf[e * 2], m1 = st.miscf[e * 2 + 1];
-  o[HRL_SF_TARGET] = m0.x; o[HRL_SF_TARGET + 1] = m0.y;
+  o[HRL_SF_TARGET] = m0.x; o[HRL_SF_TARGET + 1] = m0.y; o[HRL_SF_RETURN] = m0.z; o[HRL_SF_RETURN_SUM] = m0.w;
   o[HRL_SF_FEET] = m1.x; o[HRL_SF_FEET + 1] = m1.y; o[HRL_SF_FEET + 2] = m1.z; o[HRL_SF_FEET + 3] = m1.w;
   for (int l = 0; l < 8; l++) {
     const float4 a = st.items[e * 8 + l];
@@ -845,7 +854,7 @@ __global__ void set_state_kernel(int N, DevState st, const float* __restrict__ f
   st.base[e * 4 + 3] = make_float4(o[HRL_SF_ANGVEL], o[HRL_SF_ANGVEL + 1], o[HRL_SF_ANGVEL + 2], o[HRL_SF_WTD]);
   for (int k = 0; k < 4; k++)
     st.leg[e * 4 + k] = make_float4(o[HRL_SF_Q + 2 * k], o[HRL_SF_Q + 2 * k + 1], o[HRL_SF_QD + 2 * k], o[HRL_SF_QD + 2 * k + 1]);
-  st.miscf[e * 2] = make_float4(o[HRL_SF_TARGET], o[HRL_SF_TARGET + 1], 0.f, 0.f);
+  st.miscf[e * 2] = make_float4(o[HRL_SF_TARGET], o[HRL_SF_TARGET + 1], o[HRL_SF_RETURN], o[HRL_SF_RETURN_SUM]);
   st.miscf[e * 2 + 1] = make_float4(o[HRL_SF_FEET], o[HRL_SF_FEET + 1], o[HRL_SF_FEET + 2], o[HRL_SF_FEET + 3]);
   for (int l = 0; l < 8; l++)
     st.items[e * 8 + l] = make_float4(o[HRL_SF_ITEMS + 4 * l], o[HRL_SF_ITEMS + 4 * l + 1], o[HRL_SF_ITEMS + 4 * l + 2], o[HRL_SF_ITEMS + 4 * l + 3]);

@@ -212,6 +212,22 @@ class VecEnv:
             raise ValueError("state tensors must be [N,%d] f32 and [N,%d] i32" % (HRL_STATE_F, HRL_STATE_I))
         _cabi.check(self.L.hrl_set_state(self.h, _ptr(f), _ptr(i), self._stream()))
 
+    def episode_stats(self, aggregate=False):
+        """Episode statistics kept by the kernels: finished episodes, their mean
+        return and mean length, env-steps taken.  ``aggregate=True`` sums the counters over all ranks of the
+        default process group (NCCL over NVLink on GPUs) - the only collective this package ever issues, and
+        never on the step path."""
+        from .sharding import sum_episode_stats
+        f, i = self.get_state()
+        finished = (i[:, 1] - 1).clamp(min=0).sum().item()          # resets so far minus the running episode
+        ret_sum = f[:, 71].double().sum().item()                    # HRL_SF_RETURN_SUM
+        steps = i[:, 2].sum().item()
+        len_sum = (i[:, 2] - i[:, 0]).sum().item()                  # steps that belong to finished episodes
+        if aggregate:
+            finished, steps, ret_sum, len_sum = sum_episode_stats(finished, steps, (ret_sum, len_sum), device=self.device)
+        n = max(finished, 1)
+        return {"episodes": int(finished), "env_steps": int(steps), "mean_return": ret_sum / n, "mean_length": len_sum / n}
+
     def stats(self, reset=True):
         """In-kernel counters feeding the FLOP model: mean contacts / limit rows per env-substep."""
         out = (C.c_ulonglong * 4)()

@@ -59,7 +59,8 @@ enum {
   HRL_SF_WTD = 33,     /* cached walk_target_dist of the last calc_state             */
   HRL_SF_FEET = 34,    /* 4 feet-contact flags shown in the NEXT obs (quirk Q2)      */
   HRL_SF_ITEMS = 38,   /* 16 x (x,y): food 0-7 then poison 8-15                      */
-  HRL_SF_SPARE = 70
+  HRL_SF_RETURN = 70,      /* return of the running episode (metrics / logging)   */
+  HRL_SF_RETURN_SUM = 71   /* sum of the returns of the episodes this env has finished                */
 };
 #define HRL_STATE_I 8
 enum {

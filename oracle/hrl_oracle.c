@@ -269,6 +269,7 @@ static void ant_model_init(ant_model* M) {
 typedef struct {
   real pos[3], quat[4], vel[3], ang[3], q[8], qd[8];
   real initial_z, potential, target[2], wtd, feet[4];
+  real ret, ret_sum; /* episode-return accumulators (HRL_SF_RETURN, HRL_SF_RETURN_SUM) */
   real items[HRL_MAX_ITEMS][2];
   int32_t t, episode, steps_total, goals_left, since, rewarded;
 } env_state;
@@ -1272,7 +1273,7 @@ static void reset_env(hrlo_env* E, int e, real* obs) {
   hrl_config* cfg = &E->cfg;
   env_state* s = &E->s[e];
   int kind = cfg->env_kind;
-  s->t = 0;
+  s->t = 0; s->ret = 0;
   for (int i = 0; i < 3; i++) { s->pos[i] = (real)cfg->start_pos[i]; s->vel[i] = 0; s->ang[i] = 0; }
   s->quat[0] = s->quat[1] = s->quat[2] = 0; s->quat[3] = 1;
   for (int k = 0; k < 4; k++) s->feet[k] = 0;
@@ -1401,6 +1402,8 @@ static int step_env(hrlo_env* E, int e, const float* act, real* obs, real* rew, 
   s->steps_total++;
   /* gym TimeLimit */
   if (cfg->max_episode_steps > 0 && s->t >= cfg->max_episode_steps) { info[2] = done ? 0 : 1; done = 1; }
+  s->ret += *rew;
+  if (done) { s->ret_sum += s->ret; s->ret = 0; }
   info[3] = (real)s->t;
   return done;
 }
@@ -1549,6 +1552,7 @@ int hrlo_get_state(hrlo_env* E, real* f, int32_t* iv) {
     for (int j = 0; j < 8; j++) { o[HRL_SF_Q + j] = s->q[j]; o[HRL_SF_QD + j] = s->qd[j]; }
     o[HRL_SF_INITIAL_Z] = s->initial_z; o[HRL_SF_POTENTIAL] = s->potential;
     o[HRL_SF_TARGET] = s->target[0]; o[HRL_SF_TARGET + 1] = s->target[1]; o[HRL_SF_WTD] = s->wtd;
+    o[HRL_SF_RETURN] = s->ret; o[HRL_SF_RETURN_SUM] = s->ret_sum;
     for (int i = 0; i < HRL_MAX_ITEMS; i++) { o[HRL_SF_ITEMS + 2 * i] = s->items[i][0]; o[HRL_SF_ITEMS + 2 * i + 1] = s->items[i][1]; }
     int32_t* q = iv + (size_t)e * HRL_STATE_I;
     memset(q, 0, sizeof(int32_t) * HRL_STATE_I);
@@ -1566,6 +1570,7 @@ int hrlo_set_state(hrlo_env* E, const real* f, const int32_t* iv) {
     for (int j = 0; j < 8; j++) { s->q[j] = o[HRL_SF_Q + j]; s->qd[j] = o[HRL_SF_QD + j]; }
     s->initial_z = o[HRL_SF_INITIAL_Z]; s->potential = o[HRL_SF_POTENTIAL];
     s->target[0] = o[HRL_SF_TARGET]; s->target[1] = o[HRL_SF_TARGET + 1]; s->wtd = o[HRL_SF_WTD];
+    s->ret = o[HRL_SF_RETURN]; s->ret_sum = o[HRL_SF_RETURN_SUM];
     for (int i = 0; i < HRL_MAX_ITEMS; i++) { s->items[i][0] = o[HRL_SF_ITEMS + 2 * i]; s->items[i][1] = o[HRL_SF_ITEMS + 2 * i + 1]; }
     const int32_t* q = iv + (size_t)e * HRL_STATE_I;
     s->t = q[HRL_SI_T]; s->episode = q[HRL_SI_EPISODE]; s->steps_total = q[HRL_SI_STEPS];

@@ -418,3 +418,30 @@ def test_cube_colliders_and_contact_pickup(kw):
     if not (kw.get("robot_coll_dist", 1) > 0):
         assert events > 20, events                     # the feet do touch cubes in this set-up
     print("cube test", kw, "pickup events", events, "contacts/substep", contacts, "outliers", n_out, "/", checked)
+
+
+def test_episode_statistics_match_rewards():
+    """The in-kernel episode accumulators (HRL_SF_RETURN / HRL_SF_RETURN_SUM) equal what a user would sum up from
+    the returned rewards, and agree with the oracle's."""
+    N, T = 128, 90
+    from hrl_pybullet_envs_b200 import VecEnv
+    from oracle import oracle as O
+    g = VecEnv("AntGatherBulletEnv-v0", N, seed=8, max_episode_steps=40)
+    cfg = O.default_config(K.HRL_ANT_GATHER, N); cfg.seed = 8; cfg.max_episode_steps = 40
+    o = O.OracleVecEnv(cfg, threads=8)
+    g.reset(); o.reset()
+    gen = torch.Generator().manual_seed(4)
+    run = np.zeros(N); fin_sum = np.zeros(N); n_fin = 0
+    for t in range(T):
+        a = torch.rand(N, 8, generator=gen) * 2 - 1
+        ob, r, d, info = g.step(a.cuda())
+        o.step(a.numpy())
+        r = r.cpu().numpy().astype(np.float64); d = d.cpu().numpy()
+        run += r; fin_sum[d] += run[d]; run[d] = 0; n_fin += int(d.sum())
+    f, i = g.get_state(); fo, io = o.get_state()
+    np.testing.assert_allclose(f[:, K.SF_RETURN].cpu().numpy(), run, atol=1e-3)
+    np.testing.assert_allclose(f[:, K.SF_RETURN_SUM].cpu().numpy(), fin_sum, atol=1e-3)
+    st = g.episode_stats()
+    assert st["episodes"] == n_fin and st["env_steps"] == N * T
+    assert st["mean_return"] == pytest.approx(fin_sum.sum() / max(n_fin, 1), abs=1e-3) and 0 < st["mean_length"] <= 40
+    assert np.array_equal(i.cpu().numpy(), io)
