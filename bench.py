@@ -265,7 +265,7 @@ def run_ours(args):
             "e2e": {"value": total_envs * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": N * 8 * 4, "d2h_bytes_per_step": N * (46 * 4 + 4 + 1 + 16),
                     "api": "VecEnv.step(numpy) -> hrl_step_host, zero-copy mode: the kernel reads the actions from and writes "
-                           "obs/rew/done/info to pinned host memory over PCIe, then stream sync",
+                           "obs/rew/done/info to pinned host memory over PCIe; the host polls a completion word the last CTA publishes",
                     "value_copy_mode": total_envs * args.steps / (e2e_copy_ms * 1e-3),
                     "copy_mode": "pinned H2D memcpy, kernel, ONE packed D2H memcpy, stream sync"},
             "gpu_launches": int(launches),

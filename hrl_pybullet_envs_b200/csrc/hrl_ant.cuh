@@ -44,8 +44,9 @@
 #define HRL_CAND_F 8
 #define HRL_SMEM_FLOATS_PER_WARP (HRL_ROWS_FLOATS_PER_WARP + HRL_LAM_FLOATS_PER_WARP + HRL_MAXC * HRL_CAND_F * 32)
 
-// food / poison cube colliders (hrl_config.item_contacts): per-warp scratch [EPW][16] (x, y) + [EPW][16] contact-point counters
-#define HRL_ITEM_SCRATCH_FLOATS (HRL_EPW * 16 * 3)
+// food / poison cube colliders (hrl_config.item_contacts): per-warp scratch [EPW][16] (x, y) + [EPW] 64-bit words
+// holding 16 4-bit contact-point counters (<= 13 spheres can touch one cube)
+#define HRL_ITEM_SCRATCH_FLOATS (HRL_EPW * 16 * 2 + HRL_EPW * 2)
 
 struct AntLane {
   // replicated in the 4 lanes of an env
@@ -311,9 +312,9 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
     // per axis) are staged in shared memory with a 16-bit candidate mask per env; usually the mask is empty
     unsigned imask = 0;
     float* ixy = nullptr;
-    int* itouch = nullptr;
+    unsigned long long* itouch = nullptr;
     if (ITEMS && P.item_contacts) {
-      ixy = iscr + es * 32; itouch = reinterpret_cast<int*>(iscr + HRL_EPW * 32) + es * 16;
+      ixy = iscr + es * 32; itouch = reinterpret_cast<unsigned long long*>(iscr + HRL_EPW * 32) + es;
       const float reach = 1.1314f + 1.4143f * (P.item_half + ant::R_CAPS + P.margin);
 #pragma unroll
       for (int i = 0; i < 4; i++) {
@@ -321,8 +322,8 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
         const float dx = it_x[i] - s.O.x, dy = it_y[i] - s.O.y;
         if (gi < P.n_items && dx * dx + dy * dy < reach * reach) imask |= 1u << gi;
         ixy[2 * gi] = it_x[i]; ixy[2 * gi + 1] = it_y[i];
-        if (count_touch) itouch[gi] = 0;
       }
+      if (count_touch && k == 0) *itouch = 0ull;
       imask |= __shfl_xor_sync(HRL_FULL_MASK, imask, 1);
       imask |= __shfl_xor_sync(HRL_FULL_MASK, imask, 2);
       __syncwarp();
@@ -417,7 +418,7 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
             dist = -best - r;
           }
           if (dist < P.margin) {
-            if (count_touch) atomicAdd(&itouch[gi], 1);
+            if (count_touch) atomicAdd(itouch, 1ull << (4 * gi));
             add(crel, r, n, dist, body + 4.f);  // +4: friction class of the cubes
           }
         }

@@ -156,7 +156,8 @@ __device__ __forceinline__ bool flag_next(const hrl_config& cfg, uint32_t genv, 
 //   mode 0: full env step (+ auto-reset), mode 1: n_sub physics sub-steps only,
 //   mode 2: reset the masked envs and emit their observation, mode 3: observe only.
 // ------------------------------------------------------------------------------------------
-#define SMEM_PER_WARP_FLOATS (HRL_SMEM_FLOATS_PER_WARP + HRL_EPW * HRL_OBS_STAGE + 2 * HRL_EPW * 2 * HRL_MAX_BINS)
+#define SMEM_PER_WARP_FLOATS (HRL_SMEM_FLOATS_PER_WARP + HRL_ITEM_SCRATCH_FLOATS)
+static_assert(HRL_ROWS_FLOATS_PER_WARP >= HRL_EPW * HRL_OBS_STAGE + 2 * HRL_EPW * 2 * HRL_MAX_BINS, "task-layer tiles must fit in the row buffer");
 
 template <int FAMILY>
 __global__ void __launch_bounds__(32 * HRL_WARPS_PER_CTA)
@@ -168,8 +169,11 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, k = lane & 3, ew = lane >> 2, es = ew % HRL_EPW;
   float* rows = smem + warp * SMEM_PER_WARP_FLOATS;
   float* cands = rows + HRL_ROWS_FLOATS_PER_WARP + HRL_LAM_FLOATS_PER_WARP;
-  float* sobs = cands + HRL_MAXC * HRL_CAND_F * 32;                               // [EPW][HRL_OBS_STAGE]
-  unsigned long long* sbins = (unsigned long long*)(sobs + HRL_EPW * HRL_OBS_STAGE);   // [EPW][2][HRL_MAX_BINS]
+  // the task layer runs after the last sub-step, when the solver rows are dead: its observation staging tile and
+  // the sensor bins alias the row buffer (keeps a warp at < 37.8 KB so that 6 CTAs fit an SM at large batch sizes)
+  float* sobs = rows;                                                                   // [EPW][HRL_OBS_STAGE]
+  unsigned long long* sbins = (unsigned long long*)(rows + HRL_EPW * HRL_OBS_STAGE);   // [EPW][2][HRL_MAX_BINS]
+  float* iscr = cands + HRL_MAXC * HRL_CAND_F * 32;  // cube-collider scratch: lives across the sub-steps
   const int N = cfg.num_envs, kind = cfg.env_kind;
   const int env0 = (blockIdx.x * HRL_WARPS_PER_CTA + warp) * HRL_EPW;  // first env of this warp
   const int env_raw = env0 + ew;
@@ -221,16 +225,16 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
     const int ns = mode == 0 ? cfg.substeps : n_sub;
     for (int i = 0; i < ns; i++) {
       const bool on = (i == 0) || !cfg.torque_first_substep_only;
-      // cube colliders (FAMILY 0): scratch = the sensor-bin area, idle until the task layer; the contact points of
-      // the LAST sub-step are what getContactPoints reports (ant_gather_env.py:114)
+      // cube colliders (FAMILY 0): the contact points of the LAST sub-step are what getContactPoints reports
+      // (ant_gather_env.py:114)
       ant_substep<FAMILY == 0>(s, P, lc, on ? tau1 : 0.f, on ? tau2 : 0.f, rows, cands, lane, k, es, feet_ground, sc, sl, it_x, it_y,
-                               reinterpret_cast<float*>(sbins), mode == 0 && i == ns - 1);
+                               iscr, mode == 0 && i == ns - 1);
     }
     if (FAMILY == 0 && P.item_contacts && mode == 0) {  // this lane's 4 cubes: contact points of the last sub-step
       __syncwarp();
-      const int* itouch = reinterpret_cast<const int*>(reinterpret_cast<float*>(sbins) + HRL_EPW * 32) + es * 16;
+      const unsigned long long tw = reinterpret_cast<const unsigned long long*>(iscr + HRL_EPW * 32)[es];
 #pragma unroll
-      for (int i = 0; i < 4; i++) touch[i] = itouch[4 * k + i];
+      for (int i = 0; i < 4; i++) touch[i] = (int)((tw >> (4 * (4 * k + i))) & 15ull);
       __syncwarp();
     }
     if (st.stats) {  // warp-uniform: inactive tail lanes contribute zeros (never guard a *_sync by `active`)
@@ -1096,6 +1100,9 @@ int hrl_create(const hrl_config* cfg, int32_t device, hrl_handle** out) {
   const int smem = HRL_WARPS_PER_CTA * SMEM_PER_WARP_FLOATS * (int)sizeof(float);
   CK(cudaFuncSetAttribute(ant_env_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(ant_env_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  // the kernels live in shared memory and registers (hardly any L1 traffic): take the whole carve-out, 6 CTAs / SM
+  CK(cudaFuncSetAttribute(ant_env_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(ant_env_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   *out = h;
   // like the reference, reset() must be called before the first step(); an un-reset env has a
   // zero quaternion, produces a non-finite observation and is ended by the NaN guard
