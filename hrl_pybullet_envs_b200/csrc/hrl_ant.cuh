@@ -6,11 +6,14 @@
 //
 // Formulation (DESIGN.md "Kernel 1"): world-frame projected Newton-Euler.  The mass matrix of
 // the tree (6 base dofs + 4 legs x 2 hinges) is block-arrow: M = [[Mbb, G],[G^T, blkdiag(Mll_k)]].
-// Lane k eliminates its own leg (2x2 inverse), contributes its articulated inertia to the base
+// Lane k eliminates its own leg (2x2 Cholesky), contributes its articulated inertia to the base
 // Schur complement S (21 unique entries, summed with two xor-shuffles), every lane then holds
-// S^-1 = L^-T L^-1 in registers.  A constraint row only touches the base and ONE leg, so the
-// row response M^-1 J^T is evaluated by the owning lane alone; the projected Gauss-Seidel sweep
-// keeps the base velocity delta replicated in all 4 lanes and the leg part private to its lane.
+// L^-1 of S = L L^T in registers.  A constraint row only touches the base and ONE leg: its owner
+// lane whitens it (z = L^-1 Jb~, y = Ll^-1 Jl) and stores it at its position in Bullet's visit
+// order.  The projected Gauss-Seidel sweep then runs in the transformed velocity [L^T dvb ; Ll^T g],
+// where the same 14-vector is row Jacobian and row response; the 4 lanes of an env evaluate every
+// row redundantly from broadcast shared-memory reads (no shuffle on the dependency chain) with
+// packed FFMA2 arithmetic.
 #pragma once
 #include "hrl_math.cuh"
 #include "../../include/hrl_b200.h"

@@ -42,9 +42,6 @@ __device__ __forceinline__ float gsum(float v) {
   v += __shfl_xor_sync(HRL_FULL_MASK, v, 2);
   return v;
 }
-__device__ __forceinline__ float gbcast(float v, int lane, int owner) {
-  return __shfl_sync(HRL_FULL_MASK, v, (lane & ~3) | owner);
-}
 
 // ---- Ant model constants (reference: assets/ant.xml; derivation SURVEY.md App. C.1) --------
 // masses = 1000 kg/m^3 x volume, inertias = Bullet compound-shape AABB rule [3P-MEM]
