@@ -341,9 +341,9 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
       }
     };
 #pragma unroll 1
-    for (int si = (k == 0 ? 0 : 1); si < 4; si++) {
+    for (int si = 0; si < 4; si++) {  // same trip count in every lane: legs 1-3 see the torso slot as a null sphere
       const V3 crel = si == 0 ? mk(0.f, 0.f, 0.f) : (si == 1 ? r_tip : (si == 2 ? r_ank : K.rh));
-      const float r = si == 0 ? ant::R_TORSO : ant::R_CAPS;
+      const float r = si == 0 ? (k == 0 ? ant::R_TORSO : -1e6f) : ant::R_CAPS;  // radius -1e6: every distance is huge
       const float body = si == 1 ? 2.f : (si == 2 ? 1.f : 0.f);
       const V3 c = s.O + crel;
       const float dg = c.z - P.gz - r;

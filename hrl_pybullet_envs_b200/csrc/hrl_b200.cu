@@ -212,9 +212,12 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
   int feet_ground = 0;
   int touch[4] = {0, 0, 0, 0};
   if (mode <= 1) {
-    // the branch-free solver multiplies idle (stale) rows by 0: they must be finite
-    for (int i = lane; i < (HRL_ROWS_FLOATS_PER_WARP + HRL_LAM_FLOATS_PER_WARP) / 4; i += 32)
-      reinterpret_cast<float4*>(rows)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // idle solver visits read the two all-zero rows HRL_ROW_IDLE-1, HRL_ROW_IDLE and the impulse / mu slots
+    // behind the real ones: zero those (2 x 4 float4 per env) and the whole impulse array, nothing else
+    for (int i = lane; i < 8 * HRL_EPW; i += 32)
+      reinterpret_cast<float4*>(rows)[(i >> 3) * HRL_ENV_F4 + (HRL_ROW_IDLE - 1) * 4 + (i & 7)] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = lane; i < HRL_LAM_FLOATS_PER_WARP / 4; i += 32)
+      reinterpret_cast<float4*>(rows + HRL_ROWS_FLOATS_PER_WARP)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
     const float2 a = reinterpret_cast<const float2*>(actions)[e * 4 + k];
     act1 = a.x; act2 = a.y;
