@@ -445,3 +445,30 @@ def test_episode_statistics_match_rewards():
     assert st["episodes"] == n_fin and st["env_steps"] == N * T
     assert st["mean_return"] == pytest.approx(fin_sum.sum() / max(n_fin, 1), abs=1e-3) and 0 < st["mean_length"] <= 40
     assert np.array_equal(i.cpu().numpy(), io)
+
+
+@pytest.mark.parametrize("env_id,N", [("AntGatherBulletEnv-v0", 1), ("AntGatherBulletEnv-v0", 13), ("AntMazeBulletEnv-v0", 43),
+                                      ("PointGatherBulletEnv-v0", 5), ("PointGatherBulletEnv-v0", 131)])
+def test_ragged_batch_sizes(env_id, N):
+    """Batch sizes that do not fill the last warp / CTA (tail lanes shadow an env and must not store)."""
+    g, o = _envs(env_id, N, seed=17)
+    canary = torch.full((N + 64, g.D), 777.0, device="cuda")       # room behind the rows the kernel may not touch
+    og = g.reset().cpu().numpy(); oo = o.reset()
+    np.testing.assert_allclose(og, oo, rtol=0, atol=2e-5)
+    gen = torch.Generator().manual_seed(6)
+    for t in range(8):
+        a = torch.rand(N, g.A, generator=gen) * 2 - 1
+        f, i = g.get_state()
+        o.set_state(f.cpu().numpy().astype(np.float64), i.cpu().numpy())
+        # write the observations straight into the canary buffer through the raw C-ABI
+        rew = torch.zeros(N + 64, device="cuda"); done = torch.full((N + 64,), 9, dtype=torch.uint8, device="cuda")
+        from hrl_pybullet_envs_b200 import _cabi
+        from hrl_pybullet_envs_b200.vec_env import _ptr
+        _cabi.check(g.L.hrl_step(g.h, _ptr(a.cuda().contiguous()), _ptr(canary), _ptr(rew), _ptr(done), None, None, g._stream()))
+        oo, ro, do, io = o.step(a.numpy())
+        torch.cuda.synchronize()
+        assert (canary[N:] == 777.0).all() and (done[N:] == 9).all() and (rew[N:] == 0).all()
+        same = done[:N].cpu().numpy().astype(bool) == do
+        assert same.mean() > 0.9
+        live = same & ~do
+        assert np.abs(canary[:N].cpu().numpy()[live][:, :8] - oo[live][:, :8]).max(initial=0) < 2e-2
