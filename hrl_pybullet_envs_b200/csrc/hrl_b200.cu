@@ -140,12 +140,14 @@ struct TaskRegs {  // replicated per-env task state held in registers
 // when max_targets <= 0; the potential restarts from the STALE walk_target_dist (quirk Q3).
 // false = goal list exhausted (the reference's IndexError -> done).
 __device__ __forceinline__ bool flag_next(const hrl_config& cfg, uint32_t genv, TaskRegs& T, float px, float py, int at_reset) {
-  if (cfg.flag_max_targets < 1) flag_close_target(cfg, genv, T.steps_total, at_reset, px, py, T.tx, T.ty);
+  float gx, gy;  // out-of-line callees write to locals: T itself must stay in registers
+  if (cfg.flag_max_targets < 1) flag_close_target(cfg, genv, T.steps_total, at_reset, px, py, gx, gy);
   else {
     if (T.goals_left <= 0) return false;
     T.goals_left--;
-    flag_goal(cfg, T.episode - 1, T.goals_left, T.tx, T.ty);
+    flag_goal(cfg, T.episode - 1, T.goals_left, gx, gy);
   }
+  T.tx = gx; T.ty = gy;
   T.rewarded = 0;
   T.potential = -T.wtd / cfg.dt;
   return true;
