@@ -1172,13 +1172,14 @@ int hrl_step(hrl_handle* h, const float* d_actions, float* d_obs, float* d_rew, 
 
 /* non-NULL when `p` is pinned host memory the device can address directly (UVA): the device alias.
  * Pinned buffers are long-lived in a stepping loop, so positive answers are cached per handle. */
-static void* mapped_alias(hrl_handle* h, const void* p) {
-  for (int i = 0; i < h->alias_n; i++)
-    if (h->alias_key[i] == p) return h->alias_val[i];
+static void* mapped_alias(hrl_handle* h, const void* p, bool cache = true) {
+  if (cache)
+    for (int i = 0; i < h->alias_n; i++)
+      if (h->alias_key[i] == p) return h->alias_val[i];
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   void* d = (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
-  if (d) {
+  if (d && cache) {
     if (h->alias_n == 12) h->alias_n = 0;  // tiny ring: evict everything
     h->alias_key[h->alias_n] = p; h->alias_val[h->alias_n] = d; h->alias_n++;
   }
@@ -1198,25 +1199,31 @@ int hrl_step_host(hrl_handle* h, const float* h_actions, float* h_obs, float* h_
   cudaStream_t s = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
   const size_t N = (size_t)h->N;
+  // inputs: pinned actions are read by the kernel in place; anything else is copied H2D first
+  const float* d_act = nullptr;
+  // (action arrays come and go with the caller: asked afresh every step, never cached)
+  if (h->host_mode != HRL_HOST_COPY) d_act = (const float*)mapped_alias(h, h_actions, false);
+  if (!d_act) {
+    CK(cudaMemcpyAsync(h->s_act, h_actions, N * h->A * sizeof(float), cudaMemcpyHostToDevice, s));
+    d_act = h->s_act;
+  }
   if (h->host_mode != HRL_HOST_COPY) {
-    // zero-copy: the kernel reads the actions from and writes its results to pinned host memory over
-    // PCIe while it computes, so the transfers overlap the step instead of bracketing it
-    float* a = (float*)mapped_alias(h, h_actions);
+    // zero-copy outputs: the kernel writes its results to pinned host memory over PCIe while it computes, so the
+    // transfer overlaps the step instead of following it; completion = a word the last CTA publishes
     float* o = (float*)mapped_alias(h, h_obs);
     float* r = (float*)mapped_alias(h, h_rew);
     uint8_t* d = (uint8_t*)mapped_alias(h, h_done);
     float* i = h_info ? (float*)mapped_alias(h, h_info) : nullptr;
-    if (a && o && r && d && (i || !h_info)) {
+    if (o && r && d && (i || !h_info)) {
       const bool poll = h->h_flag && h->cfg.env_kind != HRL_POINT_GATHER;
-      int rc = launch_env(h, 0, 0, a, nullptr, o, r, d, i, nullptr, s, poll);
+      int rc = launch_env(h, 0, 0, d_act, nullptr, o, r, d, i, nullptr, s, poll);
       if (rc) return rc;
       if (!poll) CK(cudaStreamSynchronize(s));
       return HRL_OK;
     }
     if (h->host_mode == HRL_HOST_ZEROCOPY) return set_err(HRL_E_INVALID, "zero-copy host mode needs pinned (page-locked) buffers");
   }
-  CK(cudaMemcpyAsync(h->s_act, h_actions, N * h->A * sizeof(float), cudaMemcpyHostToDevice, s));
-  int rc = launch_env(h, 0, 0, h->s_act, nullptr, h->s_obs, h->s_rew, h->s_done, h->s_info, nullptr, s);
+  int rc = launch_env(h, 0, 0, d_act, nullptr, h->s_obs, h->s_rew, h->s_done, h->s_info, nullptr, s);
   if (rc) return rc;
   size_t off_rew, off_info, off_done, total;
   hrl_host_layout(&h->cfg, &off_rew, &off_info, &off_done, &total);

@@ -182,10 +182,14 @@ class VecEnv:
         if self._host is None:
             self._host = self._host_buffers()
         H = self._host
-        np.copyto(H["act_np"], np.asarray(actions).reshape(self.N, self.A), casting="same_kind")
+        if isinstance(actions, np.ndarray) and actions.dtype == np.float32 and actions.flags.c_contiguous and actions.size == self.N * self.A:
+            p_act = C.c_void_p(actions.ctypes.data)   # used in place: read over PCIe when pinned, copied H2D by the library when not
+        else:
+            np.copyto(H["act_np"], np.asarray(actions).reshape(self.N, self.A), casting="same_kind")
+            p_act = H["p_act"]
         S = H["sets"][H["flip"]]
         H["flip"] ^= 1
-        rc = self.L.hrl_step_host(self.h, H["p_act"], S["p_obs"], S["p_rew"], S["p_done"], S["p_info"], self._stream())
+        rc = self.L.hrl_step_host(self.h, p_act, S["p_obs"], S["p_rew"], S["p_done"], S["p_info"], self._stream())
         if rc:
             _cabi.check(rc)
         return S["ret"]

@@ -176,9 +176,11 @@ int hrl_step_host(hrl_handle* h, const float* h_actions, float* h_obs, float* h_
  * numpy arrays, ant_gather_env.py:76-119, so this is the whole cost of being a drop-in for it):
  *   HRL_HOST_COPY      H2D copy of the actions, kernel, D2H copies (ONE copy when the four output
  *                      buffers are carved out of one allocation as hrl_host_layout says), sync;
- *   HRL_HOST_ZEROCOPY  every buffer must be pinned: the kernel reads / writes them over PCIe while
+ *   HRL_HOST_ZEROCOPY  the output buffers must be pinned: the kernel writes them over PCIe while
  *                      it computes (transfers overlap the step), sync;
- *   HRL_HOST_AUTO      zero-copy when all buffers are pinned, else copy (default).
+ *   HRL_HOST_AUTO      zero-copy when all output buffers are pinned, else copy (default).
+ * In the last two modes a pinned action array is read in place over PCIe; a pageable one (the
+ * array a gym-style caller hands over) is copied H2D first - it is asked afresh on every call.
  * The handle caches which host pointers are pinned; calling hrl_set_host_mode (any mode) clears
  * that cache - do so after freeing a pinned buffer that was passed to hrl_step_host.
  * Calls on one handle must not overlap (the reference env is single-threaded too). */
