@@ -58,7 +58,7 @@ def main():
     dur = next(l for l in det.split("\n") if "Duration" in l).split()[-2:]
     assert len(D) == len(N), "the report was taken with a different build of libhrl_b200.so (%d vs %d instructions)" % (len(D), len(N))
     R = regions()
-    st = defaultdict(lambda: [0, 0, 0.0, 0.0])
+    st = defaultdict(lambda: [0, 0, 0.0, 0.0, defaultdict(float)])
     tot = sum(n["samples"] for n in N)
     warps = max(n["inst"] for n in N if n["inst"] > 0 and n["inst"] == int(n["inst"]))  # prologue instructions: once per warp
     warps = N[0]["inst"] or warps
@@ -70,11 +70,20 @@ def main():
                 break
         s = st[name]
         s[0] += 1; s[1] += 1 if N[i]["inst"] > 0 else 0; s[2] += N[i]["inst"]; s[3] += N[i]["samples"]
+        for kk, vv in N[i]["stalls"].items():
+            s[4][kk[6:]] += vv
     print("%s: %s, kernel %s: %.0f elapsed cycles (%s %s), %d static instructions, %d warps" % (
         os.path.basename(rep), "ncu --set full", tag, cyc, dur[1], dur[0], len(D), warps))
-    print("%-20s %7s %11s %10s %9s %6s" % ("region", "static", "exec-static", "dyn/warp", "cyc/warp", "share"))
+    print("%-20s %7s %11s %10s %9s %6s  %s" % ("region", "static", "exec-static", "dyn/warp", "cyc/warp", "share", "top stall reasons (share of the region's samples)"))
     for k, v in sorted(st.items(), key=lambda kv: -kv[1][3]):
-        print("%-20s %7d %11d %10.0f %9.0f %5.1f%%" % (k, v[0], v[1], v[2] / warps, v[3] * cyc / tot, 100 * v[3] / tot))
+        top = sorted(v[4].items(), key=lambda kv: -kv[1])[:4]
+        print("%-20s %7d %11d %10.0f %9.0f %5.1f%%  %s" % (k, v[0], v[1], v[2] / warps, v[3] * cyc / tot, 100 * v[3] / tot,
+                                                         ", ".join("%s %.0f%%" % (a, 100 * b / max(v[3], 1)) for a, b in top)))
+    allst = defaultdict(float)
+    for v in st.values():
+        for a, b in v[4].items():
+            allst[a] += b
+    print("all regions: " + ", ".join("%s %.1f%%" % (a, 100 * b / tot) for a, b in sorted(allst.items(), key=lambda kv: -kv[1])[:8]))
     print("total dyn/warp %.0f" % (sum(v[2] for v in st.values()) / warps))
 
 
