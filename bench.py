@@ -299,10 +299,17 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU,
                     help="exploration only: the BASELINE.json metric is quoted at the default 4096")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: libraries that write to fd 1 behind Python's back (the NCCL
+    # version banner does) are pointed at stderr; Python's own sys.stdout keeps the real stdout
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
