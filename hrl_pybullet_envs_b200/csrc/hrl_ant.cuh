@@ -240,11 +240,10 @@ __device__ __forceinline__ Row ld_row(const float4* __restrict__ rb, int r) {
   return R;
 }
 __device__ __forceinline__ float dot14(const float2 a[7], const float2 b[7]) {
-  // three packed accumulators: dependent depth mul, fma, fma, add2, add2, add
-  float2 s0 = mul2(a[0], b[0]), s1 = mul2(a[1], b[1]), s2 = mul2(a[2], b[2]);
-  s0 = fma2(a[3], b[3], s0); s1 = fma2(a[4], b[4], s1); s2 = fma2(a[5], b[5], s2);
-  s0 = fma2(a[6], b[6], s0);
-  const float2 t = add2(add2(s0, s1), s2);
+  // four packed accumulators: dependent depth mul, fma, add2, add2, add
+  float2 s0 = mul2(a[0], b[0]), s1 = mul2(a[1], b[1]), s2 = mul2(a[2], b[2]), s3 = mul2(a[3], b[3]);
+  s0 = fma2(a[4], b[4], s0); s1 = fma2(a[5], b[5], s1); s2 = fma2(a[6], b[6], s2);
+  const float2 t = add2(add2(s0, s1), add2(s2, s3));
   return t.x + t.y;
 }
 __device__ __forceinline__ void axpy14(float2 y[7], const float2 a[7], float s) {
@@ -259,23 +258,19 @@ __device__ __forceinline__ void axpy14(float2 y[7], const float2 a[7], float s) 
 template <bool HAS_HI>
 __device__ __forceinline__ void single_visit(float* __restrict__ lamp, float2 dv[7], const Row& R, float lam, int rl,
                                              float hi) {
-  float dl = fmaf(-dot14(R.p, dv), R.dinv, R.rhs);
-  const float sum = lam + dl;
-  if (HAS_HI) {
-    const float nl = fminf(fmaxf(sum, 0.f), hi);
-    dl = (nl == sum) ? dl : nl - lam;
-  } else {
-    dl = (sum < 0.f) ? -lam : dl;
-  }
-  lamp[rl] = lam + dl;
-  axpy14(dv, R.p, dl);
+  // new impulse = clamp(lam + rhs' - (a . dv') / (a . a)): lam + rhs' is formed off the dependency chain, which is
+  // dot -> fma -> max (-> min) -> sub -> axpy
+  float nl = fmaxf(fmaf(-dot14(R.p, dv), R.dinv, lam + R.rhs), 0.f);
+  if (HAS_HI) nl = fminf(nl, hi);
+  lamp[rl] = nl;
+  axpy14(dv, R.p, nl - lam);
 }
 // One friction pair with the implicit cone |f| <= mu * lambda_n; skipped (impulses kept) when the
 // normal impulse is zero, like Bullet.
 __device__ __forceinline__ void pair_visit(float* __restrict__ lamp, float2 dv[7], const Row& A, const Row& B, float ln,
                                            float la, float lb, int ra, float mu) {
-  float na = la + fmaf(-dot14(A.p, dv), A.dinv, A.rhs);
-  float nb = lb + fmaf(-dot14(B.p, dv), B.dinv, B.rhs);
+  float na = fmaf(-dot14(A.p, dv), A.dinv, la + A.rhs);
+  float nb = fmaf(-dot14(B.p, dv), B.dinv, lb + B.rhs);
   const float lim = mu * ln, len2 = fmaf(na, na, nb * nb);
   const float sc = (len2 > lim * lim) ? lim * rsqrt_ftz(fmaxf(len2, 1e-30f)) : 1.f;
   const bool on = ln > 0.f;
