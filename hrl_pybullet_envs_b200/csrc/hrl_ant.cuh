@@ -31,18 +31,24 @@
 //   row = a[14] | dinv | rhs  (4 x float4), a = [L^-1 Jb~ (6) ; Ll_k^-1 Jl scattered to leg k (8)]
 // so that "J M^-1 J^T" of two rows is a plain dot product and the same vector is both the row
 // Jacobian and the row response in the transformed velocity dv' = [L^T dvb ; Ll^T g].
-//   rows [0,8)   joint-limit rows (<= 2 per leg), ordered by leg
-//   rows [8,24)  contact normals, ordered by leg then candidate
-//   rows [24,56) friction pairs (2 per contact), same order
-#define HRL_ROW_NRM0 8
-#define HRL_ROW_FRI0 (8 + 4 * HRL_MAXC)
-#define HRL_ROWS_ENV (8 + 12 * HRL_MAXC)
-#define HRL_ROW_IDLE (HRL_ROWS_ENV + 1)        // rows ROWS_ENV, ROWS_ENV+1: all-zero rows / zero impulses for idle visits
-#define HRL_ENV_F4 ((HRL_ROWS_ENV + 2) * 4 + 1)  // float4 per env, +1: the env stride maps the 8 envs of a warp to distinct banks
-#define HRL_MU0 (HRL_ROWS_ENV + 2)             // per-contact friction coefficient mu[4*MAXC], in the same array as the impulses
-#define HRL_LAM_STRIDE (HRL_ROWS_ENV + 2 + 4 * HRL_MAXC + 1)  // odd: the 8 envs of a warp hit distinct banks
+//   rows [0,8)    joint-limit rows (<= 2 per leg), ordered by leg
+//   rows [8,40)   friction pairs (2 per contact): contact c at rows 8 + 2c, 9 + 2c (c ordered by leg then candidate)
+//   rows 40, 41   all-zero rows: what an idle visit reads (idle friction pair = contact slot 16 = exactly these two)
+//   rows [42,58)  contact normals, DEscending: contact c at row 57 - c, so that slot 16 lands on zero row 41
+// Every row address is affine in the contact slot, idle included: one select per visit.
+#define HRL_NSLOT (4 * HRL_MAXC)                 // contact slots per env; slot HRL_NSLOT is the idle one
+#define HRL_ROW_FRI0 8
+#define HRL_ROW_ZERO (8 + 2 * HRL_NSLOT)
+#define HRL_ROW_NRM_LAST (HRL_ROW_ZERO + 1 + HRL_NSLOT)
+#define HRL_ROWS_ENV (HRL_ROW_NRM_LAST + 1)
+#define HRL_ENV_F4 (HRL_ROWS_ENV * 4 + 1)        // float4 per env, +1: the env stride maps the 8 envs of a warp to distinct banks
+// Impulses: per contact slot one float4 (lambda_t1, lambda_t2, lambda_n, mu) - a friction visit needs all four - and
+// per env 9 limit-row impulses (slot 8 = idle).  Strides 68 (= 4 mod 32) / 9 (odd): the 8 envs of a warp hit distinct banks.
+#define HRL_CL_STRIDE (4 * (HRL_NSLOT + 1))
+#define HRL_LAML_STRIDE 9
+#define HRL_CL_FLOATS_PER_WARP (HRL_EPW * HRL_CL_STRIDE)
 #define HRL_ROWS_FLOATS_PER_WARP (HRL_EPW * HRL_ENV_F4 * 4)
-#define HRL_LAM_FLOATS_PER_WARP ((HRL_EPW * HRL_LAM_STRIDE + 3) / 4 * 4)
+#define HRL_LAM_FLOATS_PER_WARP ((HRL_CL_FLOATS_PER_WARP + HRL_EPW * HRL_LAML_STRIDE + 3) / 4 * 4)
 // contact candidates: [c][field][lane]: P-O (3), n (3), dist, body
 #define HRL_CAND_F 8
 #define HRL_SMEM_FLOATS_PER_WARP (HRL_ROWS_FLOATS_PER_WARP + HRL_LAM_FLOATS_PER_WARP + HRL_MAXC * HRL_CAND_F * 32)
@@ -181,7 +187,7 @@ __device__ __forceinline__ SubstepParams make_params(const hrl_config& cfg) {
 
 // Whiten one constraint row of leg k and store it at visit position `pos` of this env's row buffer.
 //   Jb~ = JB - K [j1 j2]^T (leg eliminated), z = L^-1 Jb~, y = Ll^-1 [j1 j2]^T, diag = |z|^2 + |y|^2.
-__device__ __forceinline__ void emit_row(float4* __restrict__ rb, float* __restrict__ lamp, int pos, int k,
+__device__ __forceinline__ void emit_row(float4* __restrict__ rb, int pos, int k,
                                          const LegDyn& D, const float JB[6], float j1, float j2, const float ub[6],
                                          float u1, float u2, float pen, float erp, float inv_h, bool positional) {
   float Jt[6], z[6];
@@ -209,7 +215,6 @@ __device__ __forceinline__ void emit_row(float4* __restrict__ rb, float* __restr
   r[1] = make_float4(z[4], z[5], k == 0 ? y0 : 0.f, k == 0 ? y1 : 0.f);
   r[2] = make_float4(k == 1 ? y0 : 0.f, k == 1 ? y1 : 0.f, k == 2 ? y0 : 0.f, k == 2 ? y1 : 0.f);
   r[3] = make_float4(k == 3 ? y0 : 0.f, k == 3 ? y1 : 0.f, dinv, (posErr + velErr) * dinv);
-  lamp[pos] = 0.f;
 }
 
 // ---- Blackwell packed fp32 (FFMA2 / FMUL2 / FADD2): two IEEE-rn fp32 operations per instruction ----
@@ -253,30 +258,28 @@ __device__ __forceinline__ void axpy14(float2 y[7], const float2 a[7], float s) 
 }
 
 // One visit of a single (non-friction) row: clamp the impulse to [0, hi], apply the delta.
-// Idle visits use the all-zero row HRL_ROW_IDLE (a = 0, dinv = rhs = 0, impulse 0): dl = 0 falls out
+// Idle visits use an all-zero row (HRL_ROW_ZERO; a = 0, dinv = rhs = 0, impulse 0): dl = 0 falls out
 // of the arithmetic, no predicate needed.
 template <bool HAS_HI>
-__device__ __forceinline__ void single_visit(float* __restrict__ lamp, float2 dv[7], const Row& R, float lam, int rl,
-                                             float hi) {
+__device__ __forceinline__ void single_visit(float* __restrict__ lp, float2 dv[7], const Row& R, float lam, float hi) {
   // new impulse = clamp(lam + rhs' - (a . dv') / (a . a)): lam + rhs' is formed off the dependency chain, which is
   // dot -> fma -> max (-> min) -> sub -> axpy
   float nl = fmaxf(fmaf(-dot14(R.p, dv), R.dinv, lam + R.rhs), 0.f);
   if (HAS_HI) nl = fminf(nl, hi);
-  lamp[rl] = nl;
+  *lp = nl;
   axpy14(dv, R.p, nl - lam);
 }
 // One friction pair with the implicit cone |f| <= mu * lambda_n; skipped (impulses kept) when the
-// normal impulse is zero, like Bullet.
-__device__ __forceinline__ void pair_visit(float* __restrict__ lamp, float2 dv[7], const Row& A, const Row& B, float ln,
-                                           float la, float lb, int ra, float mu) {
-  float na = fmaf(-dot14(A.p, dv), A.dinv, la + A.rhs);
-  float nb = fmaf(-dot14(B.p, dv), B.dinv, lb + B.rhs);
-  const float lim = mu * ln, len2 = fmaf(na, na, nb * nb);
+// normal impulse is zero, like Bullet.  c = (lambda_t1, lambda_t2, lambda_n, mu) of the contact slot at *cp.
+__device__ __forceinline__ void pair_visit(float4* __restrict__ cp, float2 dv[7], const Row& A, const Row& B, const float4 c) {
+  float na = fmaf(-dot14(A.p, dv), A.dinv, c.x + A.rhs);
+  float nb = fmaf(-dot14(B.p, dv), B.dinv, c.y + B.rhs);
+  const float lim = c.w * c.z, len2 = fmaf(na, na, nb * nb);
   const float sc = (len2 > lim * lim) ? lim * rsqrt_ftz(fmaxf(len2, 1e-30f)) : 1.f;
-  const bool on = ln > 0.f;
-  na = on ? na * sc : la; nb = on ? nb * sc : lb;
-  lamp[ra] = na; lamp[ra + 1] = nb;
-  axpy14(dv, A.p, na - la); axpy14(dv, B.p, nb - lb);
+  const bool on = c.z > 0.f;
+  na = on ? na * sc : c.x; nb = on ? nb * sc : c.y;
+  *reinterpret_cast<float2*>(cp) = make_float2(na, nb);
+  axpy14(dv, A.p, na - c.x); axpy14(dv, B.p, nb - c.y);
 }
 
 // One internal step of h = dt/substeps.  `rows`/`cands` point at this WARP's shared memory
@@ -576,7 +579,8 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
   // ---------------- constraint rows: counts, visit positions, whitened rows ----------------
   const float inv_h = P.inv_h;
   float4* __restrict__ rb = reinterpret_cast<float4*>(rows) + es * HRL_ENV_F4;  // es: this env's slot in the warp
-  float* __restrict__ lamp = rows + HRL_ROWS_FLOATS_PER_WARP + es * HRL_LAM_STRIDE;
+  float4* __restrict__ cl = reinterpret_cast<float4*>(rows + HRL_ROWS_FLOATS_PER_WARP + es * HRL_CL_STRIDE);  // contact slots
+  float* __restrict__ lamL = rows + HRL_ROWS_FLOATS_PER_WARP + HRL_CL_FLOATS_PER_WARP + es * HRL_LAML_STRIDE;     // limit impulses
   const float pl1 = s.q1 - ant::HIP_LO, ph1 = ant::HIP_HI - s.q1;
   const float pl2 = s.q2 - lc.lo2, ph2 = lc.hi2 - s.q2;
   // Bullet creates a joint-limit row iff the joint is at or beyond the limit (lo < hi: at most one per joint)
@@ -599,8 +603,9 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
       const float pl = jj ? pl2 : pl1, ph = jj ? ph2 : ph1;
       const bool lo = pl <= 0.f;
       const float sg = lo ? 1.f : -1.f, pen = lo ? pl : ph;
-      emit_row(rb, lamp, offL + (jj ? (int)lim1 : 0), k, D, zero6, jj ? 0.f : sg, jj ? sg : 0.f, ub, u1, u2, pen,
-               P.erp_l, inv_h, true);
+      const int pos = offL + (jj ? (int)lim1 : 0);
+      lamL[pos] = 0.f;
+      emit_row(rb, pos, k, D, zero6, jj ? 0.f : sg, jj ? sg : 0.f, ub, u1, u2, pen, P.erp_l, inv_h, true);
     }
   }
   for (int c = 0; c < nC; c++) {
@@ -613,7 +618,7 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
     plane_space(n, t1, t2);
     const V3 Ph = Pr - K.rh, Pa = Pr - r_ank;
     const int ci = offC + c;
-    lamp[HRL_MU0 + ci] = cube ? P.mu_item : P.mu;
+    cl[ci] = make_float4(0.f, 0.f, 0.f, cube ? P.mu_item : P.mu);
 #pragma unroll 1
     for (int di = 0; di < 3; di++) {
       const V3 d = di == 0 ? n : (di == 1 ? t1 : t2);
@@ -621,8 +626,8 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
       const float JB[6] = {jt.x, jt.y, jt.z, d.x, d.y, d.z};
       const float j1 = body >= 1.f ? dot(a1, cross(Ph, d)) : 0.f;
       const float j2 = body >= 2.f ? dot(a2, cross(Pa, d)) : 0.f;
-      const int pos = di == 0 ? HRL_ROW_NRM0 + ci : HRL_ROW_FRI0 + 2 * ci + (di - 1);
-      emit_row(rb, lamp, pos, k, D, JB, j1, j2, ub, u1, u2, dist, P.erp_c, inv_h, di == 0);
+      const int pos = di == 0 ? HRL_ROW_NRM_LAST - ci : HRL_ROW_FRI0 + 2 * ci + (di - 1);
+      emit_row(rb, pos, k, D, JB, j1, j2, ub, u1, u2, dist, P.erp_c, inv_h, di == 0);
     }
   }
   stat_contacts += nC; stat_limits += nL;
@@ -637,63 +642,61 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
 #pragma unroll
   for (int i = 0; i < 7; i++) dv[i] = make_float2(0.f, 0.f);
   const int maxNL = __reduce_max_sync(HRL_FULL_MASK, NL), maxNC = __reduce_max_sync(HRL_FULL_MASK, NC);
-#define HRL_LIM_ROW(t) (((t) < NL) ? lbase + lstep * (t) : HRL_ROW_IDLE)
-#define HRL_NRM_ROW(t) (((t) < NC) ? HRL_ROW_NRM0 + (t) : HRL_ROW_IDLE)
-#define HRL_FRI_ROW(t) (((t) < NC) ? HRL_ROW_FRI0 + 2 * (t) : HRL_ROW_IDLE - 1)
+#define HRL_LIM_ROW(t) (((t) < NL) ? lbase + lstep * (t) : HRL_ROW_ZERO)
+#define HRL_LIM_LAM(t, r) (lamL + (((t) < NL) ? (r) : 8))
+#define HRL_SLOT(t) (((t) < NC) ? (t) : HRL_NSLOT)
   for (int it = 0; it < P.iters; it++) {
     // (1) joint-limit rows; Bullet walks the non-contact rows backwards on even iterations.
     // Two visits per trip (ping-pong row registers, next row prefetched), odd tail handled apart.
     if (maxNL > 0) {
       const int lbase = (it & 1) ? 0 : NL - 1, lstep = (it & 1) ? 1 : -1;
       int r0 = HRL_LIM_ROW(0), r1;
+      float *p0 = HRL_LIM_LAM(0, r0), *p1;
       Row R0 = ld_row(rb, r0), R1;
-      float l0 = lamp[r0], l1;
+      float l0 = *p0, l1;
       int t = 0;
       for (; t + 1 < maxNL; t += 2) {
-        r1 = HRL_LIM_ROW(t + 1); R1 = ld_row(rb, r1); l1 = lamp[r1];
-        single_visit<true>(lamp, dv, R0, l0, r0, P.max_imp);
-        r0 = HRL_LIM_ROW(t + 2); R0 = ld_row(rb, r0); l0 = lamp[r0];
-        single_visit<true>(lamp, dv, R1, l1, r1, P.max_imp);
+        r1 = HRL_LIM_ROW(t + 1); p1 = HRL_LIM_LAM(t + 1, r1); R1 = ld_row(rb, r1); l1 = *p1;
+        single_visit<true>(p0, dv, R0, l0, P.max_imp);
+        r0 = HRL_LIM_ROW(t + 2); p0 = HRL_LIM_LAM(t + 2, r0); R0 = ld_row(rb, r0); l0 = *p0;
+        single_visit<true>(p1, dv, R1, l1, P.max_imp);
       }
-      if (t < maxNL) single_visit<true>(lamp, dv, R0, l0, r0, P.max_imp);
+      if (t < maxNL) single_visit<true>(p0, dv, R0, l0, P.max_imp);
     }
     if (maxNC > 0) {
-      // (2) contact normals
+      // (2) contact normals: slot c at row NRM_LAST - c, impulse in cl[c].z
       {
-        int r0 = HRL_NRM_ROW(0), r1;
-        Row R0 = ld_row(rb, r0), R1;
-        float l0 = lamp[r0], l1;
+        int c0 = HRL_SLOT(0), c1;
+        Row R0 = ld_row(rb, HRL_ROW_NRM_LAST - c0), R1;
+        float l0 = cl[c0].z, l1;
         int t = 0;
         for (; t + 1 < maxNC; t += 2) {
-          r1 = HRL_NRM_ROW(t + 1); R1 = ld_row(rb, r1); l1 = lamp[r1];
-          single_visit<false>(lamp, dv, R0, l0, r0, 0.f);
-          r0 = HRL_NRM_ROW(t + 2); R0 = ld_row(rb, r0); l0 = lamp[r0];
-          single_visit<false>(lamp, dv, R1, l1, r1, 0.f);
+          c1 = HRL_SLOT(t + 1); R1 = ld_row(rb, HRL_ROW_NRM_LAST - c1); l1 = cl[c1].z;
+          single_visit<false>(&cl[c0].z, dv, R0, l0, 0.f);
+          c0 = HRL_SLOT(t + 2); R0 = ld_row(rb, HRL_ROW_NRM_LAST - c0); l0 = cl[c0].z;
+          single_visit<false>(&cl[c1].z, dv, R1, l1, 0.f);
         }
-        if (t < maxNC) single_visit<false>(lamp, dv, R0, l0, r0, 0.f);
+        if (t < maxNC) single_visit<false>(&cl[c0].z, dv, R0, l0, 0.f);
       }
-      // (3) friction pairs
+      // (3) friction pairs: slot c at rows FRI0 + 2c, + 1; (lambda_t1, lambda_t2, lambda_n, mu) = cl[c]
       {
-        int r0 = HRL_FRI_ROW(0), r1;
-        Row A0 = ld_row(rb, r0), B0 = ld_row(rb, r0 + 1), A1, B1;
-        float n0 = lamp[HRL_NRM_ROW(0)], a0 = lamp[r0], b0 = lamp[r0 + 1], n1, a1, b1;
-        float m0 = lamp[HRL_MU0], m1;  // mu of contact t (slots of idle contacts are never read with lambda_n > 0)
+        int c0 = HRL_SLOT(0), c1;
+        Row A0 = ld_row(rb, HRL_ROW_FRI0 + 2 * c0), B0 = ld_row(rb, HRL_ROW_FRI0 + 2 * c0 + 1), A1, B1;
+        float4 q0 = cl[c0], q1;
         int t = 0;
         for (; t + 1 < maxNC; t += 2) {
-          r1 = HRL_FRI_ROW(t + 1); A1 = ld_row(rb, r1); B1 = ld_row(rb, r1 + 1);
-          n1 = lamp[HRL_NRM_ROW(t + 1)]; a1 = lamp[r1]; b1 = lamp[r1 + 1]; m1 = lamp[HRL_MU0 + t + 1];
-          pair_visit(lamp, dv, A0, B0, n0, a0, b0, r0, m0);
-          r0 = HRL_FRI_ROW(t + 2); A0 = ld_row(rb, r0); B0 = ld_row(rb, r0 + 1);
-          n0 = lamp[HRL_NRM_ROW(t + 2)]; a0 = lamp[r0]; b0 = lamp[r0 + 1]; m0 = lamp[HRL_MU0 + min(t + 2, 4 * HRL_MAXC - 1)];
-          pair_visit(lamp, dv, A1, B1, n1, a1, b1, r1, m1);
+          c1 = HRL_SLOT(t + 1); A1 = ld_row(rb, HRL_ROW_FRI0 + 2 * c1); B1 = ld_row(rb, HRL_ROW_FRI0 + 2 * c1 + 1); q1 = cl[c1];
+          pair_visit(cl + c0, dv, A0, B0, q0);
+          c0 = HRL_SLOT(t + 2); A0 = ld_row(rb, HRL_ROW_FRI0 + 2 * c0); B0 = ld_row(rb, HRL_ROW_FRI0 + 2 * c0 + 1); q0 = cl[c0];
+          pair_visit(cl + c1, dv, A1, B1, q1);
         }
-        if (t < maxNC) pair_visit(lamp, dv, A0, B0, n0, a0, b0, r0, m0);
+        if (t < maxNC) pair_visit(cl + c0, dv, A0, B0, q0);
       }
     }
   }
+#undef HRL_LIM_LAM
+#undef HRL_SLOT
 #undef HRL_LIM_ROW
-#undef HRL_NRM_ROW
-#undef HRL_FRI_ROW
   __syncwarp();
 
   // ---------------- back to physical velocities, clamp, integrate ----------------

@@ -214,10 +214,10 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
   int feet_ground = 0;
   int touch[4] = {0, 0, 0, 0};
   if (mode <= 1) {
-    // idle solver visits read the two all-zero rows HRL_ROW_IDLE-1, HRL_ROW_IDLE and the impulse / mu slots
+    // idle solver visits read the two all-zero rows HRL_ROW_ZERO, HRL_ROW_ZERO+1 and the idle impulse / mu slots
     // behind the real ones: zero those (2 x 4 float4 per env) and the whole impulse array, nothing else
     for (int i = lane; i < 8 * HRL_EPW; i += 32)
-      reinterpret_cast<float4*>(rows)[(i >> 3) * HRL_ENV_F4 + (HRL_ROW_IDLE - 1) * 4 + (i & 7)] = make_float4(0.f, 0.f, 0.f, 0.f);
+      reinterpret_cast<float4*>(rows)[(i >> 3) * HRL_ENV_F4 + HRL_ROW_ZERO * 4 + (i & 7)] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = lane; i < HRL_LAM_FLOATS_PER_WARP / 4; i += 32)
       reinterpret_cast<float4*>(rows + HRL_ROWS_FLOATS_PER_WARP)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
