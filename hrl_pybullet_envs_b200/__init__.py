@@ -7,13 +7,13 @@
 from .config import ENV_IDS, HrlConfig  # noqa: F401
 from .gym_shim import Box, make, register, registry  # noqa: F401
 
-__all__ = ["ENV_IDS", "HrlConfig", "Box", "make", "register", "registry", "VecEnv"]
+__all__ = ["ENV_IDS", "HrlConfig", "Box", "make", "register", "registry", "VecEnv", "RolloutBuffer"]
 
 
 def __getattr__(name):  # torch is only needed for the CUDA path
-    if name == "VecEnv":
-        from .vec_env import VecEnv
-        return VecEnv
+    if name in ("VecEnv", "RolloutBuffer"):
+        from . import vec_env
+        return getattr(vec_env, name)
     if name in ("gather_sensor", "sense_walls"):
         from . import vec_env
         return getattr(vec_env, name)

@@ -55,6 +55,23 @@ class LazyInfo(Mapping):
         return len(self._keys)
 
 
+class RolloutBuffer:
+    """[T, N, ...] CUDA tensors the env kernel writes into directly (the consumer side keeps the
+    observations on the device; a trainer reads obs[t] / rew[t] / done[t] without any copy in between).
+    obs has T + 1 slots: slot 0 takes the reset observation, step t writes obs[t + 1], rew[t], done[t]."""
+
+    def __init__(self, env, horizon):
+        d = env.device
+        self.T = int(horizon)
+        self.obs = torch.zeros(self.T + 1, env.N, env.D, device=d)
+        self.act = torch.zeros(self.T, env.N, env.A, device=d)
+        self.rew = torch.zeros(self.T, env.N, device=d)
+        self.done = torch.zeros(self.T, env.N, dtype=torch.bool, device=d)
+
+    def slot(self, t):
+        return self.obs[t + 1], self.rew[t], self.done[t]
+
+
 class VecEnv:
     """N independent envs of one reference id on one GPU.
 
@@ -124,8 +141,10 @@ class VecEnv:
         _cabi.check(self.L.hrl_reset(self.h, _ptr(m), _ptr(self._obs), self._stream()))
         return self._obs
 
-    def step(self, actions, want_terminal_obs=False):
-        """actions: float32 CUDA tensor [N, A] (device path) or numpy array (host path)."""
+    def step(self, actions, want_terminal_obs=False, out=None):
+        """actions: float32 CUDA tensor [N, A] (device path) or numpy array (host path).
+        ``out=(obs[N, D] f32, rew[N] f32, done[N] u8/bool)``: the kernel writes this step's results straight into
+        those CUDA tensors (e.g. slot t of a ``RolloutBuffer``) instead of the env's own buffers - no copy."""
         if isinstance(actions, np.ndarray):
             return self.step_host(actions)
         a = actions
@@ -138,9 +157,21 @@ class VecEnv:
             if self._term is None:
                 self._term = torch.zeros(self.N, self.D, device=self.device)
             term = self._term
-        _cabi.check(self.L.hrl_step(self.h, _ptr(a), _ptr(self._obs), _ptr(self._rew), _ptr(self._done),
+        obs, rew, done = self._obs, self._rew, self._done
+        if out is not None:
+            obs, rew, done = out
+            for t, shape, dts in ((obs, (self.N, self.D), (torch.float32,)), (rew, (self.N,), (torch.float32,)),
+                                  (done, (self.N,), (torch.uint8, torch.bool))):
+                if tuple(t.shape) != shape or t.dtype not in dts or not t.is_contiguous() or t.device != self.device:
+                    raise ValueError("out tensors must be contiguous CUDA tensors obs[%d,%d] f32, rew[%d] f32, done[%d] u8/bool"
+                                     % (self.N, self.D, self.N, self.N))
+        _cabi.check(self.L.hrl_step(self.h, _ptr(a), _ptr(obs), _ptr(rew), _ptr(done),
                                     _ptr(self._info), _ptr(term), self._stream()))
-        return self._obs, self._rew, self._done.view(torch.bool), self._info_dict(self._info, term)
+        return obs, rew, done.view(torch.bool), self._info_dict(self._info, term)
+
+    def rollout_buffer(self, horizon):
+        """Device-resident storage for ``horizon`` steps; ``step(a, out=buf.slot(t))`` fills slot t in place."""
+        return RolloutBuffer(self, horizon)
 
     def _info_dict(self, info, term=None):
         return LazyInfo(info, self.kind, term)

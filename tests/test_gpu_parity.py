@@ -199,7 +199,8 @@ def test_single_substep_parity(env_id):
 
 
 # ------------------------------------------------------------------ statistical rollout parity
-@pytest.mark.parametrize("env_id", ["AntGatherBulletEnv-v0", "AntMjBulletEnv-v0"])
+@pytest.mark.parametrize("env_id", ["AntGatherBulletEnv-v0", "AntMjBulletEnv-v0", "AntMazeBulletEnv-v0", "AntFlagrunBulletEnv-v0",
+                                    "PointGatherBulletEnv-v0"])
 def test_rollout_statistics(env_id):
     """Fixed-seed random-action rollouts: mean episode return / length of the CUDA path and of the
     oracle agree within 4 standard errors (trajectories themselves diverge chaotically)."""
@@ -209,7 +210,7 @@ def test_rollout_statistics(env_id):
     gen = torch.Generator().manual_seed(5)
     Rg = np.zeros(N); Ro = np.zeros(N); zg = []; zo = []
     for t in range(T):
-        a = torch.rand(N, 8, generator=gen) * 2 - 1
+        a = torch.rand(N, g.A, generator=gen) * 2 - 1
         _, r, d, _ = g.step(a.cuda()); Rg += r.cpu().numpy()
         _, r2, d2, _ = o.step(a.numpy()); Ro += r2
     fg, _ = g.get_state(); fo, _ = o.get_state()
@@ -306,6 +307,24 @@ def test_step_host_pageable_buffers_fall_back_to_copy():
     b.set_host_mode("zerocopy")
     rc = b.L.hrl_step_host(b.h, P(act), P(obs), P(rew), P(done), P(info), b._stream())
     assert rc != 0 and b"pinned" in b.L.hrl_last_error()
+
+
+def test_rollout_buffer_is_written_in_place():
+    """step(a, out=buf.slot(t)): the kernel fills the [T, N, ...] rollout tensors directly, same values as the plain path."""
+    from hrl_pybullet_envs_b200 import VecEnv
+    N, T = 96, 12
+    a = VecEnv("AntFlagrunBulletEnv-v0", N, seed=4); b = VecEnv("AntFlagrunBulletEnv-v0", N, seed=4)
+    buf = b.rollout_buffer(T)
+    buf.obs[0].copy_(b.reset()); a.reset()
+    gen = torch.Generator().manual_seed(2)
+    for t in range(T):
+        buf.act[t] = (torch.rand(N, 8, generator=gen) * 2 - 1).cuda()
+        o1, r1, d1, _ = a.step(buf.act[t])
+        o2, r2, d2, _ = b.step(buf.act[t], out=buf.slot(t))
+        assert o2.data_ptr() == buf.obs[t + 1].data_ptr()
+        assert torch.equal(o1, buf.obs[t + 1]) and torch.equal(r1, buf.rew[t]) and torch.equal(d1, buf.done[t])
+    with pytest.raises(ValueError):
+        b.step(buf.act[0], out=(buf.obs[0, : N // 2], buf.rew[0], buf.done[0]))
 
 
 def test_gym_surface():
