@@ -253,6 +253,16 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
     }
   }
 
+  // the lidar's bound lines (<= 7 x 4 floats): fetched once per warp and parked in shared memory (the contact
+  // candidates are dead by now) - the ray loop would otherwise wait for a global load per line and ray
+  if (FAMILY == 1) {
+    const float bv = (lane < 4 * n_lines) ? bounds[lane] : 0.f;
+    __syncwarp();
+    cands[lane] = bv;
+    __syncwarp();
+    bounds = cands;
+  }
+
   // ---- task layer: observation / reward / done / reset state machine ----
   // todo: 0 nothing, 1 compose+commit obs, 2 Flagrun reset stage 1 (stale-target calc_state)
   int todo = (mode == 1) ? 0 : 1;

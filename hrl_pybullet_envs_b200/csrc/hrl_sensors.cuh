@@ -84,7 +84,31 @@ __device__ __forceinline__ float lidar_ray(int i, int n_bins, float span_f, floa
   double x2 = __dadd_rn(px, __dmul_rn(range, cs)), y2 = __dadd_rn(py, __dmul_rn(range, sn));
   int sq = quadrant_d(__dsub_rn(x2, px), __dsub_rn(y2, py));
   double best = 0.0;
+  // fp32 pre-filter: with the ray written as P + t u (u = (cs, sn)), a bound line is hit at t = num / cr.  A line that
+  // is certainly farther than `range`, or certainly behind the ray (t < 0 with both ray components away from 0, i.e. the
+  // hit lies in the opposite quadrant), cannot contribute and is dropped; every other line - in particular every
+  // knife edge (near-parallel, t ~ 0, axis-aligned ray) - goes through the reference's float64 expression sequence
+  // below, so the result is bit-identical to evaluating all lines exactly.  The survivors are walked through a bit
+  // mask so that the lanes of a warp spend their float64 passes on DIFFERENT lines at the same time (trip count =
+  // the largest survivor count in the warp, typically 2-3 of 7) instead of idling through each other's lines.
+  const float csf = (float)cs, snf = (float)sn;
+  const bool clean_dir = fabsf(csf) > 1e-3f && fabsf(snf) > 1e-3f;
+  unsigned live = 0;
   for (int l = 0; l < n_lines; l++) {
+    const float x3f = bounds[4 * l], y3f = bounds[4 * l + 1], x34f = x3f - bounds[4 * l + 2], y34f = y3f - bounds[4 * l + 3];
+    const float af = x3f - pxf, bf = y3f - pyf;
+    const float n1 = af * y34f, n2 = bf * x34f, c1 = csf * y34f, c2 = snf * x34f;
+    const float num = n1 - n2, cr = c1 - c2;
+    const float en = 1e-6f * (fabsf(n1) + fabsf(n2)), ec = 1e-6f * (fabsf(c1) + fabsf(c2));
+    bool drop = false;
+    if (fabsf(cr) > 8.f * ec) {
+      drop = fabsf(num) - en > range_f * 1.0001f * (fabsf(cr) + ec);                                                         // |t| > range
+      drop = drop || (clean_dir && fabsf(num) > 8.f * en && (num < 0.f) != (cr < 0.f) && fabsf(num) > 1e-3f * fabsf(cr));  // t < 0
+    }
+    if (!drop) live |= 1u << l;
+  }
+  for (; live; live &= live - 1) {
+    const int l = __ffs(live) - 1;
     double x3 = bounds[4 * l], y3 = bounds[4 * l + 1], x4 = bounds[4 * l + 2], y4 = bounds[4 * l + 3];
     double x12 = __dsub_rn(px, x2), y12 = __dsub_rn(py, y2), x34 = __dsub_rn(x3, x4), y34 = __dsub_rn(y3, y4);
     double d = __dsub_rn(__dmul_rn(x12, y34), __dmul_rn(y12, x34));
