@@ -368,23 +368,27 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
           if (xx > P.bhi[i]) { xx = P.bhi[i]; inside = false; }
           qq[i] = xx;
         }
-        V3 n; float dist;
-        if (!inside) {
-          const V3 d = mk(cc[0] - qq[0], cc[1] - qq[1], cc[2] - qq[2]);
-          const float len = sqrtf(dot(d, d));
-          n = (1.0f / len) * d; dist = len - r;
-        } else {
-          float best = 1e30f; int bi = 0; float bs = 1.f;
+        const V3 d = mk(cc[0] - qq[0], cc[1] - qq[1], cc[2] - qq[2]);
+        const float d2 = dot(d, d), reach = r + P.margin;
+        // the common case - the sphere is nowhere near the box - leaves on the squared distance (no sqrt, no division)
+        if (inside || (reach > 0.f && d2 < reach * reach * 1.00001f)) {
+          V3 n; float dist;
+          if (!inside) {
+            const float len = sqrtf(d2);
+            n = (1.0f / len) * d; dist = len - r;
+          } else {
+            float best = 1e30f; int bi = 0; float bs = 1.f;
 #pragma unroll
-          for (int i = 0; i < 3; i++) {
-            const float dl = cc[i] - P.blo[i], dh = P.bhi[i] - cc[i];
-            if (dl < best) { best = dl; bi = i; bs = -1.f; }
-            if (dh < best) { best = dh; bi = i; bs = 1.f; }
+            for (int i = 0; i < 3; i++) {
+              const float dl = cc[i] - P.blo[i], dh = P.bhi[i] - cc[i];
+              if (dl < best) { best = dl; bi = i; bs = -1.f; }
+              if (dh < best) { best = dh; bi = i; bs = 1.f; }
+            }
+            n = mk(bi == 0 ? bs : 0.f, bi == 1 ? bs : 0.f, bi == 2 ? bs : 0.f);
+            dist = -best - r;
           }
-          n = mk(bi == 0 ? bs : 0.f, bi == 1 ? bs : 0.f, bi == 2 ? bs : 0.f);
-          dist = -best - r;
+          if (dist < P.margin) add(crel, r, n, dist, body);
         }
-        if (dist < P.margin) add(crel, r, n, dist, body);
       }
       if (ITEMS) {
         for (unsigned m = imask; m; m &= m - 1) {  // candidate cubes in index order, after ground / walls like the oracle
