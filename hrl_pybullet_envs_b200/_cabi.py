@@ -1,6 +1,6 @@
 """ctypes binding of the C-ABI shared library (include/hrl_b200.h).
 
-The library is built in-tree by ``__graft_entry__.build()`` / ``build.py`` with nvcc for
+The library is built in-tree by ``__graft_entry__.build()`` (``_cabi.build``) with nvcc for
 sm_100a.  There is NO fallback: if the library is missing or no CUDA device is present the
 calls raise.
 """
@@ -11,7 +11,7 @@ import subprocess
 from .config import HrlConfig
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# HRL_B200_LIB selects another build of the SAME sources (tuning sweeps: tools/sweep_variants.py)
+# HRL_B200_LIB selects another build of the SAME sources (A/B runs: `_cabi.build(defines=..., out=...)`, tools/gpu_round.sh)
 LIB_PATH = os.environ.get("HRL_B200_LIB") or os.path.join(_HERE, "libhrl_b200.so")
 SRC_DIR = os.path.join(_HERE, "csrc")
 INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
