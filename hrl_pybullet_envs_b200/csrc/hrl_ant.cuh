@@ -185,6 +185,47 @@ __device__ __forceinline__ SubstepParams make_params(const hrl_config& cfg) {
 
 #define CAND(c, f) cands[((c) * HRL_CAND_F + (f)) * 32 + lane]
 
+// Maze box: the cylinder part of one leg's three capsules against the box's four vertical edges (the end-spheres only
+// cover contacts at a capsule end; for a segment outside a convex rectangle the other closest pair is (rectangle
+// corner, segment interior); planar because the legs never reach the box's top).  Same order as the oracle
+// (detect_contacts): foot, aux, leg capsule x corners (lo,lo) (hi,lo) (lo,hi) (hi,hi).  Appends to the lane's
+// candidate list, returns the new count.
+__device__ __noinline__ int capsules_vs_box_edges(V3 O, V3 rh, V3 r_ank, V3 r_tip, float lox, float loy, float loz, float hix,
+                                                  float hiy, float hiz, float margin, float* __restrict__ cands, int lane, int nC) {
+#pragma unroll 1
+  for (int cap = 0; cap < 3; cap++) {
+    const V3 A = cap == 0 ? r_ank : (cap == 1 ? rh : mk(0.f, 0.f, 0.f));
+    const V3 B = cap == 0 ? r_tip : (cap == 1 ? r_ank : rh);
+    const V3 d = B - A;
+    const float L2 = d.x * d.x + d.y * d.y;
+    if (!(L2 > 1e-12f)) continue;
+    const float iL2 = 1.0f / L2;
+#pragma unroll 1
+    for (int corner = 0; corner < 4; corner++) {
+      const float cx = ((corner & 1) ? hix : lox) - O.x, sgx = (corner & 1) ? 1.f : -1.f;
+      const float cy = ((corner & 2) ? hiy : loy) - O.y, sgy = (corner & 2) ? 1.f : -1.f;
+      const float t = ((cx - A.x) * d.x + (cy - A.y) * d.y) * iL2;
+      if (!(t > 0.f && t < 1.f)) continue;
+      const V3 Q = A + t * d;
+      const float qz = O.z + Q.z;
+      if (qz < loz || qz > hiz) continue;
+      const float ex = Q.x - cx, ey = Q.y - cy;
+      if (ex * sgx < 0.f || ey * sgy < 0.f) continue;  // not in the corner's Voronoi region: a face is closer
+      const float e2 = ex * ex + ey * ey;
+      if (!(e2 > 0.f)) continue;
+      const float el = sqrtf(e2), dist = el - ant::R_CAPS;
+      if (dist < margin && nC < HRL_MAXC) {
+        const float nx = ex / el, ny = ey / el;
+        CAND(nC, 0) = Q.x - ant::R_CAPS * nx; CAND(nC, 1) = Q.y - ant::R_CAPS * ny; CAND(nC, 2) = Q.z;
+        CAND(nC, 3) = nx; CAND(nC, 4) = ny; CAND(nC, 5) = 0.f;
+        CAND(nC, 6) = dist; CAND(nC, 7) = (float)(2 - cap);
+        nC++;
+      }
+    }
+  }
+  return nC;
+}
+
 // Whiten one constraint row of leg k and store it at visit position `pos` of this env's row buffer.
 //   Jb~ = JB - K [j1 j2]^T (leg eliminated), z = L^-1 Jb~, y = Ll^-1 [j1 j2]^T, diag = |z|^2 + |y|^2.
 __device__ __forceinline__ void emit_row(float4* __restrict__ rb, int pos, int k,
@@ -428,6 +469,16 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
           }
         }
       }
+    }
+    // Maze box: the cylinder part of this leg's three capsules against the box's four vertical edges (the end-spheres
+    // above only cover contacts at a capsule end; for a segment outside a convex rectangle the other closest pair is
+    // (rectangle corner, segment interior); planar because the legs never reach the box's top).  Same order as the
+    // oracle: foot, aux, leg capsule x corners (lo,lo) (hi,lo) (lo,hi) (hi,hi).  Culled per env on the torso distance.
+    if (P.has_box) {
+      const float reach = 1.1314f + ant::R_CAPS + P.margin;  // |r_tip| <= 0.8 sqrt 2
+      const float nx = fmaxf(fmaxf(P.blo[0] - s.O.x, s.O.x - P.bhi[0]), 0.f), ny = fmaxf(fmaxf(P.blo[1] - s.O.y, s.O.y - P.bhi[1]), 0.f);
+      if (nx * nx + ny * ny < reach * reach)  // rare: out of line, off the sub-step loop's instruction footprint
+        nC = capsules_vs_box_edges(s.O, K.rh, r_ank, r_tip, P.blo[0], P.blo[1], P.blo[2], P.bhi[0], P.bhi[1], P.bhi[2], P.margin, cands, lane, nC);
     }
   }
 

@@ -453,7 +453,7 @@ static void impulse_response(const hrlo_env* E, const kin_t* K, const real f[NDO
 /* ======================================================================================
  * contacts: sphere vs ground slab top / 4 wall inner faces / maze box
  * ====================================================================================== */
-typedef struct { int sphere; v3 n, P; real dist; real mu; int item; } contact_t;
+typedef struct { int sphere; int link; v3 n, P; real dist; real mu; int item; } contact_t;
 #define MAX_CONTACT_PER_GROUP 4
 #define MAX_CONTACTS 16
 
@@ -527,7 +527,7 @@ static int detect_contacts(const hrlo_env* E, const env_state* s, const kin_t* K
       if (surf == 0 && S->foot >= 0) feet_ground[S->foot] = 1;
       if (per_group[S->group] >= MAX_CONTACT_PER_GROUP) continue;
       per_group[S->group]++;
-      C[n].sphere = si; C[n].n = nrm; C[n].dist = dist; C[n].P = vsub(c, vscale(nrm, r));
+      C[n].sphere = si; C[n].link = S->link; C[n].n = nrm; C[n].dist = dist; C[n].P = vsub(c, vscale(nrm, r));
       C[n].mu = (real)cfg->friction; C[n].item = -1;
       n++;
     }
@@ -544,9 +544,46 @@ static int detect_contacts(const hrlo_env* E, const env_state* s, const kin_t* K
         if (touched) touched[i]++;
         if (per_group[S->group] >= MAX_CONTACT_PER_GROUP) continue;
         per_group[S->group]++;
-        C[n].sphere = si; C[n].n = nrm; C[n].dist = dist; C[n].P = vsub(c, vscale(nrm, r));
+        C[n].sphere = si; C[n].link = S->link; C[n].n = nrm; C[n].dist = dist; C[n].P = vsub(c, vscale(nrm, r));
         C[n].mu = (real)cfg->item_friction; C[n].item = i;
         n++;
+      }
+    }
+    /* Maze box: the CYLINDER part of the leg's three capsules against the box's four vertical edges (the ant walks
+     * around the corners of the U, maze_scene.py:13; the end-spheres above only cover contacts at a capsule end).
+     * For a segment outside a convex rectangle the closest pair is either (segment end, rectangle) - the spheres - or
+     * (rectangle corner, segment interior) - this test; the legs never reach the box's top (z = 2), so it is planar.
+     * Runs after the last sphere of leg k (hip), order: foot, aux, leg capsule x corners (lo,lo) (hi,lo) (lo,hi) (hi,hi). */
+    if (cfg->has_box && si >= 1 && (si - 1) % 3 == 2) {
+      int k = (si - 1) / 3;
+      real sx = (real)LEG_SX[k], sy = (real)LEG_SY[k], rc = (real)ANT_R_CAPS;
+      for (int cap = 0; cap < 3; cap++) {
+        int link = 3 + 3 * k - cap;  /* foot, aux, leg */
+        real len = (cap == 0) ? (real)0.4 : (real)0.2;
+        v3 A = K->ow[link], B = vadd(A, mmulv(&K->Rw[link], V3(len * sx, len * sy, 0)));
+        v3 d = vsub(B, A);
+        real L2 = d.v[0] * d.v[0] + d.v[1] * d.v[1];
+        if (!(L2 > (real)1e-12)) continue;
+        for (int corner = 0; corner < 4; corner++) {
+          real cx = (corner & 1) ? (real)cfg->box_hi[0] : (real)cfg->box_lo[0], sgx = (corner & 1) ? (real)1 : (real)-1;
+          real cy = (corner & 2) ? (real)cfg->box_hi[1] : (real)cfg->box_lo[1], sgy = (corner & 2) ? (real)1 : (real)-1;
+          real t = ((cx - A.v[0]) * d.v[0] + (cy - A.v[1]) * d.v[1]) / L2;
+          if (!(t > 0 && t < 1)) continue;
+          v3 Q = vadd(A, vscale(d, t));
+          if (Q.v[2] < (real)cfg->box_lo[2] || Q.v[2] > (real)cfg->box_hi[2]) continue;
+          real ex = Q.v[0] - cx, ey = Q.v[1] - cy;
+          if (ex * sgx < 0 || ey * sgy < 0) continue;  /* not in the corner's Voronoi region: a face is closer */
+          real el = R_SQRT(ex * ex + ey * ey);
+          if (!(el > 0)) continue;
+          real dist = el - rc;
+          if (!(dist < margin)) continue;
+          if (per_group[k] >= MAX_CONTACT_PER_GROUP) continue;
+          per_group[k]++;
+          v3 nrm = V3(ex / el, ey / el, 0);
+          C[n].sphere = -1; C[n].link = link; C[n].n = nrm; C[n].dist = dist; C[n].P = vsub(Q, vscale(nrm, rc));
+          C[n].mu = (real)cfg->friction; C[n].item = -1;
+          n++;
+        }
       }
     }
   }
@@ -654,7 +691,7 @@ static int ant_substep(hrlo_env* E, env_state* s, const real tau[8], int feet_gr
     }
   }
   for (int c = 0; c < nc; c++) {
-    int link = M->S[C[c].sphere].link;
+    int link = C[c].link;
     row_t* r = &nrm[c];
     point_jacobian(M, &K, link, C[c].P, C[c].n, r->J);
     r->lo = 0; r->hi = (real)1e10;

@@ -177,6 +177,41 @@ def test_one_step_parity(env_id):
     assert sens_bad <= 2e-4 * max(sens_n, 1), (sens_bad, sens_n)
 
 
+def test_capsule_vs_box_corner_parity():
+    """Ants scattered around the maze-box corner (1, -2) in random poses, moving towards it: sphere AND capsule-cylinder
+    contacts with the box (hrl_ant.cuh / oracle detect_contacts) give the same sub-step on the GPU and in the oracle."""
+    N = 1024
+    g, o = _envs("AntMazeBulletEnv-v0", N, seed=3)
+    g.reset(); o.reset()
+    rng = np.random.default_rng(8)
+    f, i = g.get_state(); f = f.cpu().numpy().astype(np.float64); i = i.cpu().numpy()
+    ang = rng.uniform(-np.pi, 0.5 * np.pi, N)               # the three quadrants outside the box around the corner
+    rad = rng.uniform(0.3, 1.2, N)
+    f[:, K.SF_POS] = 1.0 + rad * np.cos(ang); f[:, K.SF_POS + 1] = -2.0 + rad * np.sin(ang)
+    inside = (f[:, K.SF_POS] < 1.3) & (f[:, K.SF_POS + 1] > -2.3)   # keep the torso sphere itself out of the box
+    f[inside, K.SF_POS] += 0.6; f[inside, K.SF_POS + 1] -= 0.6
+    f[:, K.SF_POS + 2] = rng.uniform(0.3, 0.6, N)
+    yaw = rng.uniform(-np.pi, np.pi, N)
+    f[:, K.SF_QUAT:K.SF_QUAT + 4] = np.stack([0 * yaw, 0 * yaw, np.sin(yaw / 2), np.cos(yaw / 2)], 1)
+    lo = np.array([-0.6, 0.6, -0.6, -1.6, -0.6, -1.6, -0.6, 0.6]); hi = np.array([0.6, 1.6, 0.6, -0.6, 0.6, -0.6, 0.6, 1.6])
+    f[:, K.SF_Q:K.SF_Q + 8] = rng.uniform(lo, hi, (N, 8))
+    to_corner = np.stack([1.0 - f[:, K.SF_POS], -2.0 - f[:, K.SF_POS + 1]], 1)
+    f[:, K.SF_LINVEL:K.SF_LINVEL + 2] = 1.5 * to_corner / np.linalg.norm(to_corner, axis=1, keepdims=True)
+    f[:, K.SF_LINVEL + 2] = 0; f[:, K.SF_ANGVEL:K.SF_ANGVEL + 3] = rng.normal(0, 0.5, (N, 3)); f[:, K.SF_QD:K.SF_QD + 8] = 0
+    f32 = f.astype(np.float32)
+    g.set_state(torch.tensor(f32), torch.tensor(i)); o.set_state(f32.astype(np.float64), i)
+    a = rng.uniform(-1, 1, (N, 8)).astype(np.float32)
+    c0 = o.stats()["contacts_per_substep"]
+    g.substeps(torch.tensor(a).cuda(), 1); o.substeps(a, 1)
+    fg, _ = g.get_state(); fo, _ = o.get_state()
+    ep, ev = _state_err(fg.cpu().numpy(), fo)
+    ok = (ep < POS_TOL) & (ev < VEL_TOL)
+    print(f"capsule/box corner: pos err max {ep.max():.2e}, vel err median {np.median(ev):.2e}, outside tolerance {(~ok).sum()} of {N}")
+    assert (~ok).mean() < 5e-3 and np.median(ev) < 1e-4
+    # the scene did produce box contacts (the ground is out of reach of most of these poses' hips, not of their feet)
+    assert o.stats()["contacts_per_substep"] > 0
+
+
 @pytest.mark.parametrize("env_id", ["AntGatherBulletEnv-v0", "AntMazeBulletEnv-v0"])
 def test_single_substep_parity(env_id):
     """hrl_substeps(1) against the oracle: the tightest physics comparison (no task logic)."""

@@ -148,3 +148,44 @@ def test_pickup_respawn_rule():
     for k in (0, 8):
         p = f2[:, K.SF_ITEMS + 2 * k:K.SF_ITEMS + 2 * k + 2]
         assert (np.linalg.norm(p - f2[:, K.SF_POS:K.SF_POS + 2], axis=1) >= 2.0 - 1e-3).all() and np.abs(p).max() <= 7.0
+
+
+def test_capsule_cylinder_meets_the_maze_box_corner():
+    """A foot capsule lying ACROSS the box corner (1, -2) (maze_scene.py:13: box x in [-5, 1], y in [-2, 2]) with both
+    end-spheres clear of the box: only the cylinder-vs-vertical-edge test can see it.  The ant hangs at z = 1 (no
+    ground contact); the corner contact must appear, push the leg away from the box, and vanish with has_box = 0."""
+    def run(has_box):
+        cfg = O.default_config(K.ENV_IDS["AntMazeBulletEnv-v0"], 1)
+        cfg.has_box = has_box
+        e = O.OracleVecEnv(cfg); e.reset()
+        f, i = e.get_state()
+        f[:] = 0
+        # leg 1 (front-left, direction (+1, +1)): with q = 0 its foot capsule runs from O + 0.4 (1, 1) to O + 0.8 (1, 1).
+        # Put its midpoint 0.07 m (< r = 0.08) outside the corner along the outward diagonal (+1, -1) / sqrt 2.
+        mid = np.array([1.0, -2.0]) + 0.07 * np.array([1.0, -1.0]) / np.sqrt(2.0)
+        f[0, K.SF_POS:K.SF_POS + 3] = [mid[0] - 0.6, mid[1] - 0.6, 1.0]
+        f[0, K.SF_QUAT + 3] = 1.0
+        f[0, K.SF_Q:K.SF_Q + 8] = [0, 1.6, 0, -1.6, 0, -1.6, 0, 1.6]   # other feet folded down (clear of box and ground), inside their ranges
+        f[0, K.SF_Q + 1] = 0.0                                            # ... except leg 1: straight, so the geometry above holds
+        e.set_state(f, i)
+        e.substeps(np.zeros((1, 8), np.float32), 1)
+        st = e.stats()
+        return st, e.get_state()[0][0], f[0].copy()
+    st1, f1, start = run(1)
+    st0, f0, _ = run(0)
+    # leg 1's straight ankle sits below its lower limit (30 deg): one limit row in both runs; the contact only with the box
+    assert st0["contacts_per_substep"] == 0 and st1["contacts_per_substep"] == 1
+    # the box contact is the only horizontal external force: the horizontal momentum of the whole tree (independent numpy
+    # model of test_oracle_lagrangian) stays 0 without the box and is pushed along the outward normal (+1, -1) / sqrt 2 with it
+    from test_oracle_lagrangian import links, _quat_R
+
+    def momentum(f):
+        # new velocities on the START configuration: the velocity update happens there (the position update that follows
+        # moves the lever arms, which changes sum m J u at O(h) - generalized-coordinate Euler, Bullet does the same)
+        u = np.concatenate([f[K.SF_ANGVEL:K.SF_ANGVEL + 3], f[K.SF_LINVEL:K.SF_LINVEL + 3], f[K.SF_QD:K.SF_QD + 8]])
+        return sum(m * (Jv @ u) for m, _, _, _, Jv in links(start[K.SF_POS:K.SF_POS + 3], _quat_R(start[K.SF_QUAT:K.SF_QUAT + 4]),
+                                                            start[K.SF_Q:K.SF_Q + 8]))
+    p0, p1 = momentum(f0), momentum(f1)
+    assert np.abs(p0[:2]).max() < 1e-3   # (link-constant tabulation differences of 4e-6 x a 25 rad/s limit correction)
+    n = np.array([1.0, -1.0]) / np.sqrt(2.0)
+    assert p1[:2] @ n > 0.1   # (the tangential part is friction: the foot swings under the limit correction)
