@@ -185,6 +185,66 @@ __device__ __forceinline__ SubstepParams make_params(const hrl_config& cfg) {
 
 #define CAND(c, f) cands[((c) * HRL_CAND_F + (f)) * 32 + lane]
 
+// Append one contact candidate of this lane (contact point on the robot relative to O, normal, distance, body).
+__device__ __forceinline__ int add_cand(float* __restrict__ cands, int lane, int nC, V3 crel, float r, V3 n, float dist, float body) {
+  if (nC < HRL_MAXC) {
+    const V3 Prel = crel - r * n;
+    CAND(nC, 0) = Prel.x; CAND(nC, 1) = Prel.y; CAND(nC, 2) = Prel.z;
+    CAND(nC, 3) = n.x; CAND(nC, 4) = n.y; CAND(nC, 5) = n.z;
+    CAND(nC, 6) = dist; CAND(nC, 7) = body;
+    nC++;
+  }
+  return nC;
+}
+// Sphere (centre c = O + crel, radius r) against the four wall planes at +-wx, +-wy, order +x -x +y -y like the oracle.
+__device__ __noinline__ int sphere_vs_walls(V3 c, V3 crel, float r, float body, float wx, float wy, float margin,
+                                            float* __restrict__ cands, int lane, int nC) {
+  float d;
+  d = wx - c.x - r; if (d < margin) nC = add_cand(cands, lane, nC, crel, r, mk(-1.f, 0.f, 0.f), d, body);
+  d = c.x + wx - r; if (d < margin) nC = add_cand(cands, lane, nC, crel, r, mk(1.f, 0.f, 0.f), d, body);
+  d = wy - c.y - r; if (d < margin) nC = add_cand(cands, lane, nC, crel, r, mk(0.f, -1.f, 0.f), d, body);
+  d = c.y + wy - r; if (d < margin) nC = add_cand(cands, lane, nC, crel, r, mk(0.f, 1.f, 0.f), d, body);
+  return nC;
+}
+// Sphere against an axis-aligned box (maze box, food / poison cubes): closest point outside, nearest face inside.
+// Returns the new candidate count, with bit 8 set when the sphere is within the margin (a contact POINT exists even if
+// the lane's candidate list is full - what the contact-based pickup counts).
+__device__ __forceinline__ int sphere_vs_aabb_inl(V3 c, V3 crel, float r, float body, float lox, float loy, float loz, float hix,
+                                                  float hiy, float hiz, float margin, float* __restrict__ cands, int lane, int nC) {
+  const float cc[3] = {c.x, c.y, c.z}, lo[3] = {lox, loy, loz}, hi[3] = {hix, hiy, hiz};
+  float qq[3];
+  bool inside = true;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float xx = cc[i];
+    if (xx < lo[i]) { xx = lo[i]; inside = false; }
+    if (xx > hi[i]) { xx = hi[i]; inside = false; }
+    qq[i] = xx;
+  }
+  V3 n; float dist;
+  if (!inside) {
+    const V3 d = mk(cc[0] - qq[0], cc[1] - qq[1], cc[2] - qq[2]);
+    const float len = sqrtf(dot(d, d));
+    n = (1.0f / len) * d; dist = len - r;
+  } else {
+    float best = 1e30f; int bi = 0; float bs = 1.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const float dl = cc[i] - lo[i], dh = hi[i] - cc[i];
+      if (dl < best) { best = dl; bi = i; bs = -1.f; }
+      if (dh < best) { best = dh; bi = i; bs = 1.f; }
+    }
+    n = mk(bi == 0 ? bs : 0.f, bi == 1 ? bs : 0.f, bi == 2 ? bs : 0.f);
+    dist = -best - r;
+  }
+  if (dist < margin) nC = add_cand(cands, lane, nC, crel, r, n, dist, body) | 0x100;
+  return nC;
+}
+__device__ __noinline__ int sphere_vs_aabb(V3 c, V3 crel, float r, float body, float lox, float loy, float loz, float hix,
+                                           float hiy, float hiz, float margin, float* __restrict__ cands, int lane, int nC) {
+  return sphere_vs_aabb_inl(c, crel, r, body, lox, loy, loz, hix, hiy, hiz, margin, cands, lane, nC);
+}
+
 // Maze box: the cylinder part of one leg's three capsules against the box's four vertical edges (the end-spheres only
 // cover contacts at a capsule end; for a segment outside a convex rectangle the other closest pair is (rectangle
 // corner, segment interior); planar because the legs never reach the box's top).  Same order as the oracle
@@ -370,15 +430,6 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
       imask |= __shfl_xor_sync(HRL_FULL_MASK, imask, 2);
       __syncwarp();
     }
-    auto add = [&](V3 crel, float r, V3 n, float dist, float body) {
-      if (nC < HRL_MAXC) {
-        const V3 Prel = crel - r * n;  // contact point on the robot, relative to O
-        CAND(nC, 0) = Prel.x; CAND(nC, 1) = Prel.y; CAND(nC, 2) = Prel.z;
-        CAND(nC, 3) = n.x; CAND(nC, 4) = n.y; CAND(nC, 5) = n.z;
-        CAND(nC, 6) = dist; CAND(nC, 7) = body;
-        nC++;
-      }
-    };
 #pragma unroll 1
     for (int si = 0; si < 4; si++) {  // same trip count in every lane: legs 1-3 see the torso slot as a null sphere
       const V3 crel = si == 0 ? mk(0.f, 0.f, 0.f) : (si == 1 ? r_tip : (si == 2 ? r_ank : K.rh));
@@ -388,85 +439,28 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
       const float dg = c.z - P.gz - r;
       if (dg < P.margin) {
         if (si == 1 || si == 2) feet_ground = 1;
-        add(crel, r, mk(0.f, 0.f, 1.f), dg, body);
+        nC = add_cand(cands, lane, nC, crel, r, mk(0.f, 0.f, 1.f), dg, body);
       }
-      if (P.has_walls && fminf(P.wx - fabsf(c.x), P.wy - fabsf(c.y)) - r < P.margin) {
-        float d;
-        d = P.wx - c.x - r; if (d < P.margin) add(crel, r, mk(-1.f, 0.f, 0.f), d, body);
-        d = c.x + P.wx - r; if (d < P.margin) add(crel, r, mk(1.f, 0.f, 0.f), d, body);
-        d = P.wy - c.y - r; if (d < P.margin) add(crel, r, mk(0.f, -1.f, 0.f), d, body);
-        d = c.y + P.wy - r; if (d < P.margin) add(crel, r, mk(0.f, 1.f, 0.f), d, body);
-      }
-      if (P.has_box) {
-        // sphere vs AABB
-        const float cc[3] = {c.x, c.y, c.z};
-        float qq[3];
-        bool inside = true;
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-          float xx = cc[i];
-          if (xx < P.blo[i]) { xx = P.blo[i]; inside = false; }
-          if (xx > P.bhi[i]) { xx = P.bhi[i]; inside = false; }
-          qq[i] = xx;
-        }
-        const V3 d = mk(cc[0] - qq[0], cc[1] - qq[1], cc[2] - qq[2]);
-        const float d2 = dot(d, d), reach = r + P.margin;
-        // the common case - the sphere is nowhere near the box - leaves on the squared distance (no sqrt, no division)
-        if (inside || (reach > 0.f && d2 < reach * reach * 1.00001f)) {
-          V3 n; float dist;
-          if (!inside) {
-            const float len = sqrtf(d2);
-            n = (1.0f / len) * d; dist = len - r;
-          } else {
-            float best = 1e30f; int bi = 0; float bs = 1.f;
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-              const float dl = cc[i] - P.blo[i], dh = P.bhi[i] - cc[i];
-              if (dl < best) { best = dl; bi = i; bs = -1.f; }
-              if (dh < best) { best = dh; bi = i; bs = 1.f; }
-            }
-            n = mk(bi == 0 ? bs : 0.f, bi == 1 ? bs : 0.f, bi == 2 ? bs : 0.f);
-            dist = -best - r;
-          }
-          if (dist < P.margin) add(crel, r, n, dist, body);
-        }
+      // everything but the ground is rare: the tests run out of line (off the sub-step loop's instruction footprint, which
+      // sits at the edge of the 32 KB L1.5 instruction cache), behind cheap inline culls
+      if (P.has_walls && fminf(P.wx - fabsf(c.x), P.wy - fabsf(c.y)) - r < P.margin)
+        nC = sphere_vs_walls(c, crel, r, body, P.wx, P.wy, P.margin, cands, lane, nC);
+      if (!ITEMS && P.has_box) {  // (AntGather has no box)
+        const float reach = r + P.margin;
+        const float ax = fmaxf(fmaxf(P.blo[0] - c.x, c.x - P.bhi[0]), 0.f), ay = fmaxf(fmaxf(P.blo[1] - c.y, c.y - P.bhi[1]), 0.f),
+                    az = fmaxf(fmaxf(P.blo[2] - c.z, c.z - P.bhi[2]), 0.f);
+        if (reach > 0.f && ax * ax + ay * ay + az * az < reach * reach * 1.00001f)
+          nC = sphere_vs_aabb(c, crel, r, body, P.blo[0], P.blo[1], P.blo[2], P.bhi[0], P.bhi[1], P.bhi[2], P.margin, cands, lane, nC) & 0xff;
       }
       if (ITEMS) {
         for (unsigned m = imask; m; m &= m - 1) {  // candidate cubes in index order, after ground / walls like the oracle
           const int gi = __ffs(m) - 1;
           const float bx = ixy[2 * gi], by = ixy[2 * gi + 1], hh = P.item_half, rr = hh + r + P.margin;
           if (fabsf(c.x - bx) > rr || fabsf(c.y - by) > rr) continue;
-          const float lo[3] = {bx - hh, by - hh, P.item_z - hh}, hi[3] = {bx + hh, by + hh, P.item_z + hh};
-          const float cc[3] = {c.x, c.y, c.z};
-          float qq[3];
-          bool inside = true;
-#pragma unroll
-          for (int i = 0; i < 3; i++) {
-            float xx = cc[i];
-            if (xx < lo[i]) { xx = lo[i]; inside = false; }
-            if (xx > hi[i]) { xx = hi[i]; inside = false; }
-            qq[i] = xx;
-          }
-          V3 n; float dist;
-          if (!inside) {
-            const V3 d = mk(cc[0] - qq[0], cc[1] - qq[1], cc[2] - qq[2]);
-            const float len = sqrtf(dot(d, d));
-            n = (1.0f / len) * d; dist = len - r;
-          } else {
-            float best = 1e30f; int bi = 0; float bs = 1.f;
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-              const float dl = cc[i] - lo[i], dh = hi[i] - cc[i];
-              if (dl < best) { best = dl; bi = i; bs = -1.f; }
-              if (dh < best) { best = dh; bi = i; bs = 1.f; }
-            }
-            n = mk(bi == 0 ? bs : 0.f, bi == 1 ? bs : 0.f, bi == 2 ? bs : 0.f);
-            dist = -best - r;
-          }
-          if (dist < P.margin) {
-            if (count_touch) atomicAdd(itouch, 1ull << (4 * gi));
-            add(crel, r, n, dist, body + 4.f);  // +4: friction class of the cubes
-          }
+          nC = sphere_vs_aabb(c, crel, r, body + 4.f /* friction class of the cubes */, bx - hh, by - hh, P.item_z - hh, bx + hh, by + hh,
+                              P.item_z + hh, P.margin, cands, lane, nC);
+          if (count_touch && (nC & 0x100)) atomicAdd(itouch, 1ull << (4 * gi));
+          nC &= 0xff;
         }
       }
     }
@@ -474,7 +468,7 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
     // above only cover contacts at a capsule end; for a segment outside a convex rectangle the other closest pair is
     // (rectangle corner, segment interior); planar because the legs never reach the box's top).  Same order as the
     // oracle: foot, aux, leg capsule x corners (lo,lo) (hi,lo) (lo,hi) (hi,hi).  Culled per env on the torso distance.
-    if (P.has_box) {
+    if (!ITEMS && P.has_box) {
       const float reach = 1.1314f + ant::R_CAPS + P.margin;  // |r_tip| <= 0.8 sqrt 2
       const float nx = fmaxf(fmaxf(P.blo[0] - s.O.x, s.O.x - P.bhi[0]), 0.f), ny = fmaxf(fmaxf(P.blo[1] - s.O.y, s.O.y - P.bhi[1]), 0.f);
       if (nx * nx + ny * ny < reach * reach)  // rare: out of line, off the sub-step loop's instruction footprint
