@@ -17,8 +17,11 @@ SRC_DIR = os.path.join(_HERE, "csrc")
 INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
 _lib = None
 
+# -prec-div / -prec-sqrt off: fp32 divisions and square roots become MUFU + one Newton step (2 ulp) without their IEEE
+# slow paths - fewer instruction bytes per launch (43.9 -> 43.15 us), every parity test unchanged; float64 (the sensor
+# decisions, the lidar) is not affected by these switches
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC", "-prec-div=false", "-prec-sqrt=false"]
 
 # every symbol include/hrl_b200.h declares (checked by tests/test_cabi_symbols.py)
 SYMBOLS = ["hrl_default_config", "hrl_obs_dim", "hrl_act_dim", "hrl_create", "hrl_destroy", "hrl_reset", "hrl_step",
