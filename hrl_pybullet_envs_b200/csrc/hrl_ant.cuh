@@ -185,6 +185,14 @@ __device__ __forceinline__ SubstepParams make_params(const hrl_config& cfg) {
 
 #define CAND(c, f) cands[((c) * HRL_CAND_F + (f)) * 32 + lane]
 
+// exp(w h) of the quaternion update for |w| h > pi/4 (needs max_coord_vel > 110): Bullet's literal path with its angle
+// cap, (sin(y)/|w|, cos(y)).  Never taken at the default clamp; out of line (results by value, in registers) so that
+// sinf / cosf stay off the sub-step loop's instruction footprint.
+__device__ __noinline__ float2 quat_exp_literal(float w2, float h) {
+  float ang = sqrtf(w2);
+  if (ang * h > 0.25f * 3.14159265358979323846f) ang = 0.25f * 3.14159265358979323846f / h;
+  return make_float2(sinf(0.5f * ang * h) / ang, cosf(0.5f * ang * h));
+}
 // Append one contact candidate of this lane (contact point on the robot relative to O, normal, distance, body).
 __device__ __forceinline__ int add_cand(float* __restrict__ cands, int lane, int nC, V3 crel, float r, V3 n, float dist, float body) {
   if (nC < HRL_MAXC) {
@@ -780,9 +788,8 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
       kk = 0.5f * P.h * fmaf(y2, fmaf(y2, fmaf(y2, fmaf(y2, 2.7557319e-6f, -1.9841270e-4f), 8.3333333e-3f), -0.16666667f), 1.f);
       cw = fmaf(y2, fmaf(y2, fmaf(y2, fmaf(y2, 2.4801587e-5f, -1.3888889e-3f), 4.1666667e-2f), -0.5f), 1.f);
     } else {
-      float ang = sqrtf(w2);
-      if (ang * P.h > 0.25f * 3.14159265358979323846f) ang = 0.25f * 3.14159265358979323846f / P.h;
-      kk = sinf(0.5f * ang * P.h) / ang; cw = cosf(0.5f * ang * P.h);
+      const float2 e = quat_exp_literal(w2, P.h);
+      kk = e.x; cw = e.y;
     }
     const float ax = s.w.x * kk, ay = s.w.y * kk, az = s.w.z * kk;
     const float x = s.qx, y = s.qy, z = s.qz, qw = s.qw;
