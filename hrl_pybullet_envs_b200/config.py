@@ -93,9 +93,7 @@ def apply_kwargs(cfg, kind, kw):
         if "respawn" in kw:
             cfg.respawn = int(bool(kw.pop("respawn")))
         if "use_sensor" in kw:
-            cfg.use_sensor = int(bool(kw.pop("use_sensor")))  # False: get_abs_pos, ant_gather_env.py:179-196
-            if not cfg.use_sensor and kind == HRL_POINT_GATHER:
-                raise NotImplementedError(_UNSUPPORTED % ("use_sensor", False))
+            cfg.use_sensor = int(bool(kw.pop("use_sensor")))  # False: get_abs_pos, ant_gather_env.py:179-196 / gather_base.py:170-187
         if "item_contacts" in kw:      # extension kwarg: switch the cube colliders (default on for AntGather) off / on
             cfg.item_contacts = int(bool(kw.pop("item_contacts")))
             if kind == HRL_POINT_GATHER and cfg.item_contacts:

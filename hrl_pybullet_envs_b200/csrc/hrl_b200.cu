@@ -788,10 +788,31 @@ point_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const floa
       for (int q = 1; q < 8; q++) v = (j == q) ? o8[q] : v;
       sobs[eb][j] = v;
     }
-    for (int b = j; b < 2 * nb; b += 16) {
-      const int ty = b / nb, bb = b - ty * nb;
-      const unsigned long long bits = sb[eb][ty][bb];
-      sobs[eb][8 + b] = bits == 0x7ff0000000000000ull ? 0.f : (float)(1.0 - __longlong_as_double((long long)bits) / (double)cfg.sensor_range);
+    if (cfg.use_sensor) {
+      for (int b = j; b < 2 * nb; b += 16) {
+        const int ty = b / nb, bb = b - ty * nb;
+        const unsigned long long bits = sb[eb][ty][bb];
+        sobs[eb][8 + b] = bits == 0x7ff0000000000000ull ? 0.f : (float)(1.0 - __longlong_as_double((long long)bits) / (double)cfg.sensor_range);
+      }
+    } else {
+      // use_sensor=False -> get_abs_pos (gather_base.py:170-187): world xy of the min(n_bins, n) nearest food items, then
+      // poison items, each sorted by squared distance (stable).  Lane j's rank = number of same-type items that sort
+      // before its own; the 16 exact float64 distances go round the half-warp by shuffle.
+      const double dx = __dsub_rn((double)it.x, (double)pos.x), dy = __dsub_rn((double)it.y, (double)pos.y);
+      const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+      const bool poison = j >= cfg.n_food;
+      int rank = 0;
+#pragma unroll 1
+      for (int o = 0; o < 16; o++) {
+        const double od = __shfl_sync(HRL_FULL_MASK, d2, o, 16);
+        const bool same = o < n_items && ((o >= cfg.n_food) == poison);
+        rank += (same && (od < d2 || (od == d2 && o < j))) ? 1 : 0;
+      }
+      const int keep_f = min(nb, cfg.n_food), keep_p = min(nb, cfg.n_poison);
+      if (has_item && rank < (poison ? keep_p : keep_f)) {
+        const int at = 8 + (poison ? 2 * keep_f : 0) + 2 * rank;
+        sobs[eb][at] = it.x; sobs[eb][at + 1] = it.y;
+      }
     }
     __syncwarp();
     bool emit = work && (mode != 1);
@@ -1045,7 +1066,6 @@ static int validate(const hrl_config* c) {
   if (c->n_food < 0 || c->n_food > 8 || c->n_poison < 0 || c->n_poison > 8) return set_err(HRL_E_INVALID, "n_food/n_poison out of range");
   if (c->substeps < 1 || c->solver_iters < 0) return set_err(HRL_E_INVALID, "bad substeps/solver_iters");
   if (c->n_targets > HRL_MAX_TARGETS || c->flag_max_targets > 127) return set_err(HRL_E_INVALID, "too many targets");
-  if (c->env_kind == HRL_POINT_GATHER && !c->use_sensor) return set_err(HRL_E_INVALID, "PointGather use_sensor=False is not built");
   if (c->env_kind == HRL_POINT_GATHER && (c->item_contacts || !(c->robot_coll_dist > 0.f)))
     return set_err(HRL_E_INVALID, "PointGather cube colliders / contact-based pickup are not built");
   if (c->env_kind == HRL_ANT_GATHER && !(c->robot_coll_dist > 0.f) && !c->item_contacts)

@@ -220,15 +220,18 @@ def gen_flagrun_goals():
 
 
 # --------------------------------------------------------------------------- 7. AntGather.step task layer
-def gen_gather_step(rng):
+GATHER_STEP_CASES = [("ant", AntGatherBulletEnv, 10, 28), ("point", GatherBulletEnv, 5, 8),
+                     ("antabs", AntGatherBulletEnv, 5, 28)]  # antabs: use_sensor=False -> get_abs_pos
+
+
+def gen_gather_step(rng, cases=GATHER_STEP_CASES, out="gather_step.npz"):
     """Whole `AntGatherBulletEnv.step` / `GatherBulletEnv.step` with a stub robot: given the
     post-physics robot state (calc_state output, torso pose) and the item table, the reference
     computes pickups, respawns, the sensor, alive/done and the reward."""
     M = 400
     fake = _ref_stubs.FakeBullet()
     res = {}
-    for tag, cls, n_bins, sdim in [("ant", AntGatherBulletEnv, 10, 28), ("point", GatherBulletEnv, 5, 8),
-                                   ("antabs", AntGatherBulletEnv, 5, 28)]:  # antabs: use_sensor=False -> get_abs_pos
+    for tag, cls, n_bins, sdim in cases:
         state = f32(rng.uniform(-1, 1, size=(M, sdim)))
         xyz = f32(np.concatenate([rng.uniform(-7, 7, size=(M, 2)), rng.uniform(0.15, 0.9, size=(M, 1))], axis=1))
         rpy = f32(rng.uniform(-math.pi, math.pi, size=(M, 3)) * [0.2, 0.2, 1.0])
@@ -257,7 +260,7 @@ def gen_gather_step(rng):
                        alive_bonus=alive, initial_z=initial_z, body_rpy=rpy[m], robot_body=torso, objects=[0])
             stub = NS(robot=robot, scene=NS(global_step=lambda: None), stadium_scene=sc, parts={"torso": torso},
                       robot_body=torso, robot_coll_dist=1, n_bins=n_bins, sensor_span=np.pi, sensor_range=20.0,
-                      use_sensor=(tag != "antabs"), dying_cost=-10, debug=False, FOOD="food", POISON="poison", _p=fake)
+                      use_sensor=not tag.endswith("abs"), dying_cost=-10, debug=False, FOOD="food", POISON="poison", _p=fake)
             stub.sq_dist_robot = lambda pos, stub=stub: cls.sq_dist_robot(stub, pos)
             stub.get_food_obs = lambda d, stub=stub: cls.get_food_obs(stub, d)
             stub.get_sensor_readings = lambda d, stub=stub: cls.get_sensor_readings(stub, d)
@@ -275,7 +278,7 @@ def gen_gather_step(rng):
                     f"{tag}_done": np.array(DONE), f"{tag}_food_rew": np.array(FR, dtype=np.float64),
                     f"{tag}_dead_rew": np.array(DR, dtype=np.float64), f"{tag}_new_objs": np.array(NEWO),
                     f"{tag}_used": np.array(USED)})
-    np.savez_compressed(os.path.join(HERE, "gather_step.npz"), **res)
+    np.savez_compressed(os.path.join(HERE, out), **res)
 
 
 # --------------------------------------------------------------------------- 8. AntMaze.step task layer
@@ -426,6 +429,9 @@ if __name__ == "__main__":
     gen_random_on_plane(rng)
     gen_flagrun_goals()
     gen_gather_step(rng)
+    # added later, with its own generator so that the files above stay byte-identical: PointGather use_sensor=False
+    # (GatherBulletEnv.get_abs_pos, gather_base.py:170-187), 4 nearest food + 4 nearest poison items
+    gen_gather_step(np.random.default_rng(20261019), cases=[("pointabs", GatherBulletEnv, 4, 8)], out="gather_step_pointabs.npz")
     gen_maze_step(rng)
     gen_flagrun_step(rng)
     gen_robots(rng)

@@ -71,9 +71,9 @@ def test_kwargs_mapping():
     K.apply_kwargs(cfg, K.HRL_ANT_GATHER, dict(item_contacts=False, robot_coll_dist=0))   # contact-based pickup needs them
     assert cfg.item_contacts == 1
     p = _cabi.default_config(K.HRL_POINT_GATHER, 1)
+    K.apply_kwargs(p, K.HRL_POINT_GATHER, dict(use_sensor=False, n_bins=4))   # gather_base.py:170-187
+    assert p.use_sensor == 0 and K.obs_dim(p) == 8 + 2 * 4 + 2 * 4
     with pytest.raises(NotImplementedError):                             # still outside the built scope: fail loudly
-        K.apply_kwargs(p, K.HRL_POINT_GATHER, dict(use_sensor=False))
-    with pytest.raises(NotImplementedError):
         K.apply_kwargs(_cabi.default_config(K.HRL_POINT_GATHER, 1), K.HRL_POINT_GATHER, dict(robot_coll_dist=0))
     f = _cabi.default_config(K.HRL_ANT_FLAGRUN, 1)
     K.apply_kwargs(f, K.HRL_ANT_FLAGRUN, dict(use_sensor=True, sensor_bins=6, switch_flag_on_collision=False))

@@ -379,6 +379,7 @@ def test_gym_surface():
 # ------------------------------------------------------------------ non-default ctor kwargs
 KWARG_CASES = [
     ("AntGatherBulletEnv-v0", dict(use_sensor=False, n_bins=5)),            # get_abs_pos, ant_gather_env.py:179-196
+    ("PointGatherBulletEnv-v0", dict(use_sensor=False, n_bins=4)),          # get_abs_pos, gather_base.py:170-187
     ("AntGatherBulletEnv-v0", dict(respawn=False, n_bins=6, sensor_range=12.0)),
     ("AntMazeBulletEnv-v0", dict(sense_target=True)),                       # ant_maze_bullet_env.py:135-178
     ("AntMazeBulletEnv-v0", dict(max_steps=20, done_at_target=False, targ_dist_rew=True, inner_rew_weight=0.3)),

@@ -80,15 +80,15 @@ def test_random_on_plane(golden):
 
 
 @pytest.mark.parametrize("tag,kind,nbase,can_die", [("ant", K.HRL_ANT_GATHER, 26, 1), ("point", K.HRL_POINT_GATHER, 8, 0),
-                                                    ("antabs", K.HRL_ANT_GATHER, 26, 1)])
+                                                    ("antabs", K.HRL_ANT_GATHER, 26, 1), ("pointabs", K.HRL_POINT_GATHER, 8, 0)])
 def test_gather_step_task_layer(golden, tag, kind, nbase, can_die):
     """Whole reference AntGather/PointGather `step` task layer (pickups, respawn rule with
     replayed uniforms, sensor, alive/done, reward, info)."""
-    g = golden("gather_step.npz")
+    g = golden("gather_step_pointabs.npz" if tag == "pointabs" else "gather_step.npz")
     L = O.lib()
     cfg = O.default_config(kind, 1)
-    if tag == "antabs":  # use_sensor=False: xy of the n_bins nearest food / poison items (ant_gather_env.py:179-196)
-        cfg.use_sensor = 0; cfg.n_bins = 5
+    if tag.endswith("abs"):  # use_sensor=False: xy of the n_bins nearest food / poison items (ant_gather_env.py:179-196)
+        cfg.use_sensor = 0; cfg.n_bins = 5 if tag == "antabs" else 4
     nb = K.food_obs_dim(cfg) // 2
     bad = 0
     for m in range(len(g[f"{tag}_state"])):
