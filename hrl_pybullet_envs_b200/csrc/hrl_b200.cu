@@ -1038,7 +1038,7 @@ int hrl_obs_dim(const hrl_config* c) {
     case HRL_ANT_FLAGRUN: return 28 + (c->flag_use_sensor ? c->n_bins : 0);  // ant_flagrun_env.py:52-54
     case HRL_ANT_MJ: return 29;                                          // MjAnt.py:15
     case HRL_ANT_MAZE_MJ: return 29 + 3 * c->n_bins + 1;                 // ant_maze_mj_env.py:50
-    case HRL_POINT_GATHER: return 8 + 2 * c->n_bins;                     // gather_base.py:54-55
+    case HRL_POINT_GATHER: return 8 + food_obs_dim(c);                   // gather_base.py:54-55,170-187
   }
   return -1;
 }
