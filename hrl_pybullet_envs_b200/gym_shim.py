@@ -61,15 +61,18 @@ class SingleEnv:
         return self.vec.reset().cpu().numpy()[0].copy()
 
     def step(self, a):
-        import torch
-        act = torch.as_tensor(np.asarray(a, dtype=np.float32).reshape(1, -1), device=self.vec.device)
-        obs, rew, done, info = self.vec.step(act)
-        i = {k: (v[0].item() if v.ndim == 1 else v[0].cpu().numpy()) for k, v in info.items()}
-        if not i.pop("TimeLimit.truncated"):
-            pass
-        else:
-            i["TimeLimit.truncated"] = True
-        return obs.cpu().numpy()[0].copy(), float(rew[0].item()), bool(done[0].item()), i
+        # numpy in / numpy out through hrl_step_host: ONE launch, results land in pinned host memory (no torch ops,
+        # no per-value device synchronisation)
+        act = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(1, -1))
+        obs, rew, done, info = self.vec.step_host(act)
+        i = {}
+        for k, v in info.items():
+            if k == "TimeLimit.truncated":
+                if bool(v[0]):
+                    i[k] = True
+            elif k != "terminal_obs":
+                i[k] = float(v[0])
+        return obs[0].copy(), float(rew[0]), bool(done[0]), i
 
     def render(self, *a, **k):
         return None  # headless batched simulator: no renderer
