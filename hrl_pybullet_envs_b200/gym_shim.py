@@ -70,6 +70,8 @@ class SingleEnv:
             if k == "TimeLimit.truncated":
                 if bool(v[0]):
                     i[k] = True
+            elif k == "target":
+                i[k] = (float(v[0, 0]), float(v[0, 1]))
             elif k != "terminal_obs":
                 i[k] = float(v[0])
         return obs[0].copy(), float(rew[0]), bool(done[0]), i

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .config import (ENV_IDS, HRL_STATE_F, HRL_STATE_I, HRL_ANT_FLAGRUN, HRL_ANT_GATHER, HRL_POINT_GATHER, apply_kwargs)
+from .config import (ENV_IDS, HRL_STATE_F, HRL_STATE_I, HRL_ANT_FLAGRUN, HRL_ANT_GATHER, HRL_POINT_GATHER, SF_TARGET, apply_kwargs)
 
 
 def _ptr(t):
@@ -24,12 +24,14 @@ class LazyInfo(Mapping):
     besides the env kernel.  Keys follow the reference: ant_gather_env.py:119 ('food_rew',
     'dead_rew'), gym TimeLimit ('TimeLimit.truncated')."""
 
-    def __init__(self, raw, kind, term=None):
-        self.raw, self._kind, self._term = raw, kind, term
+    def __init__(self, raw, kind, term=None, env=None):
+        self.raw, self._kind, self._term, self._env = raw, kind, term, env
         keys = ["TimeLimit.truncated", "episode_length"]
         keys += ["food_rew", "dead_rew"] if kind in (HRL_ANT_GATHER, HRL_POINT_GATHER) else ["inner_rew"]
         if kind == HRL_ANT_FLAGRUN:
             keys.append("goals_left")
+            if env is not None:
+                keys.append("target")   # ant_flagrun_env.py:188,199: i['target'] = self.goal (here: the current goal of every env)
         if term is not None:
             keys.append("terminal_obs")
         self._keys = keys
@@ -46,6 +48,10 @@ class LazyInfo(Mapping):
             return r[:, 0]
         if k in ("dead_rew", "goals_left"):
             return r[:, 1]
+        if k == "target":  # read from the state on access (one small kernel + copy, only when somebody looks)
+            f, _ = self._env.get_state()
+            t = f[:, SF_TARGET:SF_TARGET + 2]
+            return t.cpu().numpy() if isinstance(r, np.ndarray) else t
         return self._term
 
     def __iter__(self):
@@ -174,7 +180,7 @@ class VecEnv:
         return RolloutBuffer(self, horizon)
 
     def _info_dict(self, info, term=None):
-        return LazyInfo(info, self.kind, term)
+        return LazyInfo(info, self.kind, term, env=self)
 
     HOST_MODES = {"auto": 0, "copy": 1, "zerocopy": 2}
 
@@ -202,7 +208,7 @@ class VecEnv:
                 p_obs=C.c_void_p(base), p_rew=C.c_void_p(base + o_rew.value), p_info=C.c_void_p(base + o_info.value),
                 p_done=C.c_void_p(base + o_done.value)))
         for S in sets:
-            S["info_map"] = LazyInfo(S["info"], self.kind)
+            S["info_map"] = LazyInfo(S["info"], self.kind, env=self)
             S["ret"] = (S["obs"], S["rew"], S["done"], S["info_map"])
         act = torch.zeros(self.N, self.A, pin_memory=True)
         return dict(sets=sets, act=act, act_np=act.numpy(), p_act=C.c_void_p(act.data_ptr()), flip=0)

@@ -360,6 +360,10 @@ def test_rollout_buffer_is_written_in_place():
         assert torch.equal(o1, buf.obs[t + 1]) and torch.equal(r1, buf.rew[t]) and torch.equal(d1, buf.done[t])
     with pytest.raises(ValueError):
         b.step(buf.act[0], out=(buf.obs[0, : N // 2], buf.rew[0], buf.done[0]))
+    # Flagrun's info['target'] (ant_flagrun_env.py:188,199): the current goal of every env, read from the state on access
+    _, _, _, info = a.step(buf.act[0])
+    f, _ = a.get_state()
+    assert torch.equal(info["target"], f[:, K.SF_TARGET:K.SF_TARGET + 2]) and (info["target"].abs() <= 5.0).all()
 
 
 def test_gym_surface():
