@@ -290,6 +290,42 @@ def test_full_size_properties():
     assert torch.equal(f, f2) and torch.equal(i, i2)
 
 
+@pytest.mark.parametrize("env_id,N", [("AntMazeBulletEnv-v0", 4096), ("AntFlagrunBulletEnv-v0", 16384)])
+def test_full_size_properties_walker_family(env_id, N):
+    """BASELINE.json configs 4 and 5 at their full sizes: determinism, the multi-GPU shard rule (two half batches with
+    env_index_offset == the full batch, bit for bit) and the task invariants that do not need the oracle."""
+    from hrl_pybullet_envs_b200 import VecEnv
+    a = VecEnv(env_id, N, seed=5); b = VecEnv(env_id, N, seed=5)
+    c0 = VecEnv(env_id, N // 2, seed=5, env_index_offset=0); c1 = VecEnv(env_id, N // 2, seed=5, env_index_offset=N // 2)
+    oa = a.reset().clone(); ob = b.reset().clone(); oc = torch.cat([c0.reset(), c1.reset()])
+    assert torch.equal(oa, ob) and torch.equal(oa, oc)
+    gen = torch.Generator().manual_seed(3)
+    n_done = 0
+    for t in range(120):
+        act = (torch.rand(N, 8, generator=gen) * 2 - 1).cuda()
+        oa, ra, da, ia = a.step(act); ob, rb, db, _ = b.step(act)
+        o0, r0, d0, _ = c0.step(act[: N // 2]); o1, r1, d1, _ = c1.step(act[N // 2:])
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)
+        assert torch.equal(oa, torch.cat([o0, o1])) and torch.equal(ra, torch.cat([r0, r1])) and torch.equal(da, torch.cat([d0, d1]))
+        assert torch.isfinite(oa).all() and torch.isfinite(ra).all()
+        n_done += int(da.sum())
+        if env_id.startswith("AntMaze"):
+            assert ((ra == 0) | (ra == 1)).all()                       # inner reward weight 0, +1 at the goal (ant_maze_bullet_env.py:84-89)
+            assert (oa[:, 28:] >= 0).all() and (oa[:, 28:] <= 1).all()  # wall lidar intensities
+            assert ((oa[:, 26:28].norm(dim=1) - 1).abs() < 1e-4).all() # unit goal direction
+        else:
+            assert (ia["target"].abs() <= 5.0).all()                   # goals ~ U(-5, 5)^2 (ant_flagrun_env.py:71-78)
+            assert (ia["goals_left"] <= 100).all() and (ia["goals_left"] >= 0).all()
+    f, i = a.get_state()
+    assert (i[:, K.SI_STEPS] == 120).all()
+    if env_id.startswith("AntMaze"):
+        tg = f[:, K.SF_TARGET:K.SF_TARGET + 2]
+        allowed = torch.tensor([[2., -3.], [2., 0.], [2., 3.], [-2., 4.]], device=tg.device)   # ant_maze_bullet_env.py:13-14
+        assert ((tg[:, None, :] - allowed[None]).abs().sum(-1).min(dim=1).values == 0).all()
+    else:
+        assert (i[:, K.SI_SINCE] <= 120).all()
+
+
 def test_time_limit_and_auto_reset():
     from hrl_pybullet_envs_b200 import VecEnv
     N = 64
