@@ -48,6 +48,7 @@ class HrlConfig(C.Structure):
         ("sense_target", C.c_int32), ("maze_max_steps", C.c_int32), ("targ_dist_rew", C.c_int32),
         ("flag_use_sensor", C.c_int32), ("flag_switch_on_collision", C.c_int32), ("flag_max_target_dist", C.c_float),
         ("item_contacts", C.c_int32), ("item_friction", C.c_float), ("item_half", C.c_float), ("item_z", C.c_float),
+        ("flag_manual_goals", C.c_int32),
     ]
 
     def copy(self):
@@ -167,10 +168,11 @@ def apply_kwargs(cfg, kind, kw):
             cfg.sensor_span = float(kw.pop("sensor_span"))
         if "sensor_range" in kw:
             cfg.sensor_range = float(kw.pop("sensor_range"))
-        for name, default in (("enclosed", True), ("manual_goal_creation", False)):
-            if name in kw and kw[name] != default:
-                raise NotImplementedError(_UNSUPPORTED % (name, kw[name]))
-            kw.pop(name, None)
+        if "manual_goal_creation" in kw:   # ant_flagrun_env.py:150-153: reset() creates no goals; VecEnv.set_target / create_targets
+            cfg.flag_manual_goals = int(bool(kw.pop("manual_goal_creation")))
+        if "enclosed" in kw and kw["enclosed"] is not True:
+            raise NotImplementedError(_UNSUPPORTED % ("enclosed", kw["enclosed"]))
+        kw.pop("enclosed", None)
         if cfg.flag_max_targets > 127:
             raise ValueError("max_targets must be <= 127")
     if kw:

@@ -310,8 +310,9 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
         if (kind == HRL_ANT_MJ) { T.tx = 1000.f; T.ty = 0.f; }
         if (kind == HRL_ANT_FLAGRUN) {
           if (T.episode == 0) { T.tx = 1000.f; T.ty = 0.f; }  // WalkerBase default walk target
-          T.goals_left = cfg.flag_max_targets; T.rewarded = 0;
-          todo = 2;
+          T.rewarded = 0;
+          if (cfg.flag_manual_goals) { T.goals_left = 0; set_pot = true; todo = 1; }  // ant_flagrun_env.py:150-153: no goals drawn, target kept
+          else { T.goals_left = cfg.flag_max_targets; todo = 2; }
         } else { set_pot = true; todo = 1; }
       }
       T.episode++;
@@ -1267,6 +1268,35 @@ int hrl_step_host(hrl_handle* h, const float* h_actions, float* h_obs, float* h_
     if (h_info) CK(cudaMemcpyAsync(h_info, h->s_info, N * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
   }
   CK(cudaStreamSynchronize(s));
+  return HRL_OK;
+}
+
+// AntFlagrunBulletEnv.next_target() as a public call (ant_flagrun_env.py:112-120; the step calls it by itself on
+// reach / timeout): pops the next goal of the masked envs, resets `_rewarded`, restarts the potential from the stale
+// walk_target_dist (quirk Q3).  Envs whose goal list is empty keep their target (the reference raises IndexError).
+__global__ void flag_next_kernel(const __grid_constant__ hrl_config cfg, DevState st, const uint8_t* __restrict__ mask) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= cfg.num_envs || (mask && !mask[e])) return;
+  const float4 b0 = st.base[e * 4 + 0], b2 = st.base[e * 4 + 2], b3 = st.base[e * 4 + 3];
+  float4 m0 = st.miscf[e * 2 + 0];
+  int4 i0 = st.misci[e * 2 + 0], i1 = st.misci[e * 2 + 1];
+  TaskRegs T;
+  T.initial_z = b0.w; T.potential = b2.w; T.wtd = b3.w; T.tx = m0.x; T.ty = m0.y; T.ret = m0.z; T.ret_sum = m0.w;
+  T.t = i0.x; T.episode = i0.y; T.steps_total = i0.z; T.goals_left = i0.w; T.since = i1.x; T.rewarded = i1.y;
+  if (!flag_next(cfg, (uint32_t)(cfg.env_index_offset + e), T, b0.x, b0.y, 0)) return;
+  st.base[e * 4 + 2] = make_float4(b2.x, b2.y, b2.z, T.potential);
+  st.miscf[e * 2 + 0] = make_float4(T.tx, T.ty, m0.z, m0.w);
+  st.misci[e * 2 + 0] = make_int4(i0.x, i0.y, i0.z, T.goals_left);
+  st.misci[e * 2 + 1] = make_int4(0, T.rewarded, i1.z, i1.w);  // steps_since_goal_change = 0 (ant_flagrun_env.py:190,201)
+}
+
+int hrl_flagrun_next_target(hrl_handle* h, const uint8_t* d_mask, void* stream) {
+  if (!h) return set_err(HRL_E_INVALID, "null handle");
+  if (h->cfg.env_kind != HRL_ANT_FLAGRUN) return set_err(HRL_E_INVALID, "hrl_flagrun_next_target: not an AntFlagrun handle");
+  CK(cudaSetDevice(h->device));
+  flag_next_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->cfg, h->st, d_mask);
+  g_launches++;
+  CK(cudaGetLastError());
   return HRL_OK;
 }
 

@@ -76,6 +76,21 @@ class SingleEnv:
                 i[k] = float(v[0])
         return obs[0].copy(), float(rew[0]), bool(done[0]), i
 
+    # AntFlagrunBulletEnv's public goal methods (ant_flagrun_env.py:57,91-120); TypeError on the other envs
+    @property
+    def goal(self):
+        g = self.vec.goal[0]
+        return (float(g[0]), float(g[1]))
+
+    def set_target(self, x, y):
+        self.vec.set_target([float(x), float(y)])
+
+    def create_targets(self, n):
+        self.vec.create_targets(n)
+
+    def next_target(self):
+        return self.vec.next_target().cpu().numpy()[0].copy()
+
     def render(self, *a, **k):
         return None  # headless batched simulator: no renderer
 

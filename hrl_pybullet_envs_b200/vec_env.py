@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .config import (ENV_IDS, HRL_STATE_F, HRL_STATE_I, HRL_ANT_FLAGRUN, HRL_ANT_GATHER, HRL_POINT_GATHER, SF_TARGET, apply_kwargs)
+from .config import (ENV_IDS, HRL_STATE_F, HRL_STATE_I, HRL_ANT_FLAGRUN, HRL_ANT_GATHER, HRL_POINT_GATHER, SF_TARGET, SI_GOALS_LEFT, apply_kwargs)
 
 
 def _ptr(t):
@@ -238,6 +238,47 @@ class VecEnv:
     def substeps(self, actions, n_sub):
         a = actions.to(device=self.device, dtype=torch.float32).contiguous()
         _cabi.check(self.L.hrl_substeps(self.h, _ptr(a), int(n_sub), self._stream()))
+
+    # ------------------------------------------------------------------ Flagrun goal API (ant_flagrun_env.py:91-120)
+    def _flagrun_only(self):
+        if self.kind != HRL_ANT_FLAGRUN:
+            raise TypeError("only AntFlagrunBulletEnv has walk targets to set")
+
+    @property
+    def goal(self):
+        """Current walk target of every env, [N, 2] (ant_flagrun_env.py:57 `goal`)."""
+        self._flagrun_only()
+        return self.get_state()[0][:, SF_TARGET:SF_TARGET + 2]
+
+    def set_target(self, xy, env_ids=None):
+        """set_target(x, y) (ant_flagrun_env.py:98-110) for all envs or `env_ids`: moves the walk target only - like the
+        reference it neither touches the potential nor `_rewarded` (next_target does)."""
+        self._flagrun_only()
+        f, i = self.get_state()
+        xy = torch.as_tensor(xy, dtype=torch.float32, device=self.device)
+        if env_ids is None:
+            f[:, SF_TARGET:SF_TARGET + 2] = xy
+        else:
+            f[torch.as_tensor(env_ids, device=self.device), SF_TARGET:SF_TARGET + 2] = xy
+        self.set_state(f, i)
+
+    def create_targets(self, n=None):
+        """create_targets(n) (ant_flagrun_env.py:91-96): refill every env's goal list with n (default max_targets) goals
+        of the shared stream; the step pops them on reach / timeout, `next_target()` pops one now."""
+        self._flagrun_only()
+        n = self.cfg.flag_max_targets if n is None else int(n)
+        if not 0 <= n <= 127:
+            raise ValueError("n must be in [0, 127]")
+        f, i = self.get_state()
+        i[:, SI_GOALS_LEFT] = n
+        self.set_state(f, i)
+
+    def next_target(self, mask=None):
+        """next_target() (ant_flagrun_env.py:112-120) for all envs or the masked ones; returns the fresh observation."""
+        self._flagrun_only()
+        m = None if mask is None else torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        _cabi.check(self.L.hrl_flagrun_next_target(self.h, _ptr(m), self._stream()))
+        return self.observe()
 
     # ------------------------------------------------------------------ checkpoint / resume
     def get_state(self):

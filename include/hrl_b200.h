@@ -138,6 +138,8 @@ typedef struct hrl_config {
   float item_friction;       /* 1.5 (ant.xml:9) x 0.5 (Bullet default of the cube URDF) [3P-MEM]               */
   float item_half;           /* 0.125                                                                         */
   float item_z;              /* 0.1 (gather_scene.py:62)                                                      */
+  int32_t flag_manual_goals; /* ant_flagrun_env.py:16,150-153 manual_goal_creation: reset() draws no goals and keeps the
+                              * current walk target; the caller sets goals (VecEnv.set_target / create_targets)    */
 } hrl_config;
 
 typedef struct hrl_handle hrl_handle;
@@ -199,6 +201,13 @@ int hrl_get_state(hrl_handle* h, float* d_fstate, int32_t* d_istate, void* strea
 int hrl_set_state(hrl_handle* h, const float* d_fstate, const int32_t* d_istate, void* stream);
 /* Observation of the current state without stepping (reset()'s return path). */
 int hrl_observe(hrl_handle* h, float* d_obs, void* stream);
+
+/* AntFlagrunBulletEnv.next_target() (ant_flagrun_env.py:112-120) for the envs with d_mask[e] != 0 (NULL: all): pop the
+ * next pre-drawn goal (or draw a close one when max_targets <= 0), clear `_rewarded`, restart the potential, zero
+ * steps_since_goal_change.  With manual_goal_creation (hrl_config.flag_manual_goals) this, together with writing
+ * HRL_SF_TARGET / HRL_SI_GOALS_LEFT through hrl_set_state (set_target :98-110, create_targets :91-96), is how the
+ * caller drives the goals; envs with an empty goal list are left untouched (the reference raises IndexError). */
+int hrl_flagrun_next_target(hrl_handle* h, const uint8_t* d_mask, void* stream);
 
 /* ---- stand-alone parity entry points (stateless) --------------------------------------- */
 /* Gather sector sensor, ant_gather_env.py:128-177 / gather_base.py:118-168.

@@ -1337,9 +1337,14 @@ static void reset_env(hrlo_env* E, int e, real* obs) {
     if (s->episode == 0) { s->target[0] = 1000; s->target[1] = 0; } /* WalkerBase default walk target */
     ant_calc_state(E, s, &c);
     s->wtd = c.wtd;
-    s->goals_left = cfg->flag_max_targets;
     s->rewarded = 0;
-    flag_next_target(E, e, s, s->episode, &c, 1);
+    if (cfg->flag_manual_goals) { /* :150-153: goals.clear(), nothing drawn, the walk target stays; potential as in WalkerBase.reset */
+      s->goals_left = 0;
+      s->potential = -s->wtd / (real)cfg->dt;
+    } else {
+      s->goals_left = cfg->flag_max_targets;
+      flag_next_target(E, e, s, s->episode, &c, 1);
+    }
   } else if (is_ant(kind)) {
     ant_calc_state(E, s, &c);
     s->wtd = c.wtd;

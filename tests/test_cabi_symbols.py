@@ -80,8 +80,11 @@ def test_kwargs_mapping():
     assert f.flag_use_sensor == 1 and f.flag_switch_on_collision == 0 and K.obs_dim(f) == 34
     with pytest.raises(AssertionError):                                  # ant_flagrun_env.py:17-18
         K.apply_kwargs(_cabi.default_config(K.HRL_ANT_FLAGRUN, 1), K.HRL_ANT_FLAGRUN, dict(max_target_dist=3.0))
-    with pytest.raises(NotImplementedError):
-        K.apply_kwargs(_cabi.default_config(K.HRL_ANT_FLAGRUN, 1), K.HRL_ANT_FLAGRUN, dict(manual_goal_creation=True))
+    g = _cabi.default_config(K.HRL_ANT_FLAGRUN, 1)
+    K.apply_kwargs(g, K.HRL_ANT_FLAGRUN, dict(manual_goal_creation=True))   # ant_flagrun_env.py:150-153
+    assert g.flag_manual_goals == 1
+    with pytest.raises(NotImplementedError):                             # the pybullet_envs stadium scene is not built
+        K.apply_kwargs(_cabi.default_config(K.HRL_ANT_FLAGRUN, 1), K.HRL_ANT_FLAGRUN, dict(enclosed=False))
     m = _cabi.default_config(K.HRL_ANT_MAZE, 1)
     K.apply_kwargs(m, K.HRL_ANT_MAZE, dict(targets=([1, 2], [3, 4]), tol=2.0, target_encoding=1))
     assert m.n_targets == 2 and m.targets[1][0] == 3.0 and m.tol == 2.0 and m.target_encoding == 1

@@ -402,6 +402,40 @@ def test_rollout_buffer_is_written_in_place():
     assert torch.equal(info["target"], f[:, K.SF_TARGET:K.SF_TARGET + 2]) and (info["target"].abs() <= 5.0).all()
 
 
+def test_flagrun_manual_goals_api():
+    """manual_goal_creation=True (ant_flagrun_env.py:150-153) with the public goal methods: reset() draws nothing and keeps
+    the WalkerBase default target; set_target moves it; create_targets + next_target pop the shared stream exactly like the
+    automatic mode does at reset; an empty list ends the episode on the per-goal timeout (IndexError -> done, :196-202)."""
+    from hrl_pybullet_envs_b200 import VecEnv
+    N = 64
+    m = VecEnv("AntFlagrunBulletEnv-v0", N, seed=3, manual_goal_creation=True, timeout=5)
+    auto = VecEnv("AntFlagrunBulletEnv-v0", N, seed=3, timeout=5)
+    m.reset(); auto.reset()
+    assert torch.equal(m.goal, torch.tensor([1000.0, 0.0], device="cuda").expand(N, 2))
+    fm, im = m.get_state()
+    assert (im[:, K.SI_GOALS_LEFT] == 0).all()
+    m.set_target([2.0, -1.5])
+    assert torch.equal(m.goal, torch.tensor([2.0, -1.5], device="cuda").expand(N, 2))
+    m.set_target([0.5, 0.25], env_ids=[3])
+    assert m.goal[3].tolist() == [0.5, 0.25] and m.goal[4].tolist() == [2.0, -1.5]
+    # create_targets + next_target == what the automatic mode did inside reset(): same goal, same goals_left
+    m.create_targets()
+    obs = m.next_target()
+    fa, ia = auto.get_state(); fm, im = m.get_state()
+    assert torch.equal(fm[:, K.SF_TARGET:K.SF_TARGET + 2], fa[:, K.SF_TARGET:K.SF_TARGET + 2])
+    assert torch.equal(im[:, K.SI_GOALS_LEFT], ia[:, K.SI_GOALS_LEFT]) and (im[:, K.SI_GOALS_LEFT] == 99).all()
+    assert torch.allclose(obs, auto.observe(), atol=1e-6)
+    # empty list: the 5-step per-goal timeout finds nothing to pop -> done
+    e = VecEnv("AntFlagrunBulletEnv-v0", N, seed=3, manual_goal_creation=True, timeout=5, auto_reset=False)
+    e.reset()
+    z = torch.zeros(N, 8, device="cuda")
+    for t in range(5):
+        _, _, done, _ = e.step(z)
+        assert bool(done.all()) == (t == 4)
+    with pytest.raises(TypeError):
+        VecEnv("AntMjBulletEnv-v0", 4).set_target([0.0, 0.0])
+
+
 def test_gym_surface():
     import hrl_pybullet_envs_b200 as hrl
     for env_id, D, A in [("AntGatherBulletEnv-v0", 46, 8), ("AntMazeBulletEnv-v0", 38, 8), ("AntFlagrunBulletEnv-v0", 28, 8),
@@ -427,6 +461,7 @@ KWARG_CASES = [
     ("AntGatherBulletEnv-v0", dict(robot_coll_dist=0)),                     # contact-based pickup, ant_gather_env.py:113-116
     ("AntGatherBulletEnv-v0", dict(item_contacts=False)),                   # cube colliders off (they are on by default)
     ("AntFlagrunBulletEnv-v0", dict(use_sensor=True)),                      # ant_flagrun_env.py:122-130
+    ("AntFlagrunBulletEnv-v0", dict(manual_goal_creation=True)),            # ant_flagrun_env.py:150-153: no goals drawn at reset
     ("AntFlagrunBulletEnv-v0", dict(switch_flag_on_collision=False, timeout=15, max_targets=3, tolerance=2.5)),
     ("AntFlagrunBulletEnv-v0", dict(max_targets=0, max_target_dist=4.0, tolerance=1.5, timeout=10)),  # create_close_target :80-89
 ]
