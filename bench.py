@@ -41,6 +41,15 @@ def ncu_traffic():
         return None
 
 
+def ncu_warp_instructions():
+    """Warp-instructions per launch of the dominant kernel from the same committed capture, or None."""
+    p = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    try:
+        return json.load(open(p))["warp_instructions_per_launch"]
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -62,8 +71,8 @@ def cpu_port_rate(seconds=12.0, n_envs=ENVS_PER_GPU, threads=None):
     env.reset()
     rng = np.random.default_rng(0)
     acts = rng.uniform(-1, 1, (8, n_envs, 8)).astype(np.float32)
-    for i in range(2):
-        env.step(acts[i])
+    for i in range(40):   # land first (see run_reference)
+        env.step(acts[i % 8])
     t0 = time.perf_counter(); k = 0
     while True:
         env.step(acts[k % 8]); k += 1
@@ -93,7 +102,9 @@ def run_reference(args):
     env.reset()
     rng = np.random.default_rng(0)
     acts = rng.uniform(-1, 1, (16, n, 8)).astype(np.float32)
-    for i in range(args.warmup):
+    # like the GPU arm's warm-up: let the ants land first (reset drops them 0.3 m, ~15 steps without any contact row),
+    # so that even a short --steps/--warmup run times steps with the contacts active
+    for i in range(max(args.warmup, 40)):
         env.step(acts[i % 16])
     t0 = time.perf_counter()
     for i in range(args.steps):
@@ -282,6 +293,14 @@ def run_ours(args):
                               "flop_per_env_step": flops, "contacts_per_substep": stats["contacts_per_substep"],
                               "limit_rows_per_substep": stats["limit_rows_per_substep"]},
         }
+        wi = ncu_warp_instructions() if N == ENVS_PER_GPU else None
+        if wi:
+            # third view of the same launch: share of the machine's instruction-issue slots (4 schedulers x 148 SMs, one
+            # warp-instruction per cycle each) - the kernel is integer / branch / shared-memory work around packed FMAs
+            issue_peak = 148 * 4 * sm_max * 1e6
+            out["roofline_issue"] = {"bound": "issue", "achieved": wi / launch_s / 1e9, "peak": issue_peak / 1e9, "unit": "Gwarp-inst/s",
+                                     "frac": wi / launch_s / issue_peak, "warp_instructions_per_launch": wi,
+                                     "source": "ncu smsp__inst_executed.sum of the committed capture (profiles/), launch time measured live"}
         if cpu_v is not None:
             out["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": cpu_c, "kind": "port", "sample": cpu_s}
         print(json.dumps(out))
