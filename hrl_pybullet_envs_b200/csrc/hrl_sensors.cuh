@@ -107,21 +107,30 @@ __device__ __forceinline__ float lidar_ray(int i, int n_bins, float span_f, floa
     }
     if (!drop) live |= 1u << l;
   }
+  // the nearest accepted hit wins (1 - dist / range is monotone in dist, and so is the square root): the survivors only
+  // track the smallest squared distance; one sqrt and one division per ray, after the loop, give the same double as
+  // max over lines of 1 - sqrt(dd) / range.  (A hit with sqrt(dd) == range exactly yields 0 and never beats `best`,
+  // so testing dd against range^2 cannot change the result either.)
+  const double x12 = __dsub_rn(px, x2), y12 = __dsub_rn(py, y2), c12 = __dsub_rn(__dmul_rn(px, y2), __dmul_rn(py, x2));
+  const double range2 = __dmul_rn(range, range);
+  double best_dd = -1.0;
   for (; live; live &= live - 1) {
     const int l = __ffs(live) - 1;
     double x3 = bounds[4 * l], y3 = bounds[4 * l + 1], x4 = bounds[4 * l + 2], y4 = bounds[4 * l + 3];
-    double x12 = __dsub_rn(px, x2), y12 = __dsub_rn(py, y2), x34 = __dsub_rn(x3, x4), y34 = __dsub_rn(y3, y4);
+    double x34 = __dsub_rn(x3, x4), y34 = __dsub_rn(y3, y4);
     double d = __dsub_rn(__dmul_rn(x12, y34), __dmul_rn(y12, x34));
     if (d == 0.0) continue;
-    double c12 = __dsub_rn(__dmul_rn(px, y2), __dmul_rn(py, x2));
     double c34 = __dsub_rn(__dmul_rn(x3, y4), __dmul_rn(y3, x4));
     double ix = __ddiv_rn(__dsub_rn(__dmul_rn(c12, x34), __dmul_rn(x12, c34)), d);
     double iy = __ddiv_rn(__dsub_rn(__dmul_rn(c12, y34), __dmul_rn(y12, c34)), d);
     double ddx = __dsub_rn(px, ix), ddy = __dsub_rn(py, iy);
-    double dist = sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
-    if (dist > range) continue;
+    double dd = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
+    if (dd > range2 && sqrt(dd) > range) continue;   // (the sqrt only runs in the sliver where the two tests could differ)
     if (sq != quadrant_d(__dsub_rn(ix, px), __dsub_rn(iy, py))) continue;
-    double val = 1.0 - dist / range;
+    if (best_dd < 0.0 || dd < best_dd) best_dd = dd;
+  }
+  if (best_dd >= 0.0) {
+    const double val = 1.0 - sqrt(best_dd) / range;
     if (val > best) best = val;
   }
   return (float)best;
