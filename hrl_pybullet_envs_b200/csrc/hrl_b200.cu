@@ -1287,7 +1287,7 @@ __global__ void flag_next_kernel(const __grid_constant__ hrl_config cfg, DevStat
   st.base[e * 4 + 2] = make_float4(b2.x, b2.y, b2.z, T.potential);
   st.miscf[e * 2 + 0] = make_float4(T.tx, T.ty, m0.z, m0.w);
   st.misci[e * 2 + 0] = make_int4(i0.x, i0.y, i0.z, T.goals_left);
-  st.misci[e * 2 + 1] = make_int4(0, T.rewarded, i1.z, i1.w);  // steps_since_goal_change = 0 (ant_flagrun_env.py:190,201)
+  st.misci[e * 2 + 1] = make_int4(i1.x, T.rewarded, i1.z, i1.w);  // steps_since_goal_change is the step's business (:190,201), not next_target's
 }
 
 int hrl_flagrun_next_target(hrl_handle* h, const uint8_t* d_mask, void* stream) {

@@ -203,8 +203,8 @@ int hrl_set_state(hrl_handle* h, const float* d_fstate, const int32_t* d_istate,
 int hrl_observe(hrl_handle* h, float* d_obs, void* stream);
 
 /* AntFlagrunBulletEnv.next_target() (ant_flagrun_env.py:112-120) for the envs with d_mask[e] != 0 (NULL: all): pop the
- * next pre-drawn goal (or draw a close one when max_targets <= 0), clear `_rewarded`, restart the potential, zero
- * steps_since_goal_change.  With manual_goal_creation (hrl_config.flag_manual_goals) this, together with writing
+ * next pre-drawn goal (or draw a close one when max_targets <= 0), clear `_rewarded`, restart the potential
+ * (steps_since_goal_change is left alone, like the reference's method).  With manual_goal_creation (hrl_config.flag_manual_goals) this, together with writing
  * HRL_SF_TARGET / HRL_SI_GOALS_LEFT through hrl_set_state (set_target :98-110, create_targets :91-96), is how the
  * caller drives the goals; envs with an empty goal list are left untouched (the reference raises IndexError). */
 int hrl_flagrun_next_target(hrl_handle* h, const uint8_t* d_mask, void* stream);
