@@ -23,7 +23,7 @@ HRL_STATE_I = 8
 SF_POS, SF_QUAT, SF_LINVEL, SF_ANGVEL, SF_Q, SF_QD = 0, 3, 7, 10, 13, 21
 SF_INITIAL_Z, SF_POTENTIAL, SF_TARGET, SF_WTD, SF_FEET, SF_ITEMS = 29, 30, 31, 33, 34, 38
 SF_RETURN, SF_RETURN_SUM = 70, 71
-SI_T, SI_EPISODE, SI_STEPS, SI_GOALS_LEFT, SI_SINCE, SI_REWARDED = range(6)
+SI_T, SI_EPISODE, SI_STEPS, SI_GOALS_LEFT, SI_SINCE, SI_REWARDED, SI_GOAL_GEN = range(7)
 
 
 class HrlConfig(C.Structure):
@@ -124,10 +124,6 @@ def apply_kwargs(cfg, kind, kw):
             cfg.tol = float(kw.pop("tol"))
         if "inner_rew_weight" in kw:
             cfg.inner_rew_weight = float(kw.pop("inner_rew_weight"))
-        if "seed" in kw:
-            s = kw.pop("seed")
-            if s is not None:
-                cfg.seed = int(s)
         if kind == HRL_ANT_MAZE:
             if "sense_walls" in kw:
                 cfg.sense_walls = int(bool(kw.pop("sense_walls")))
@@ -150,8 +146,6 @@ def apply_kwargs(cfg, kind, kw):
             cfg.flag_max_targets = int(kw.pop("max_targets"))
         if "timeout" in kw:
             cfg.flag_timeout = int(kw.pop("timeout"))
-        if "seed" in kw:
-            cfg.flag_seed = int(kw.pop("seed"))
         if "max_target_dist" in kw:
             cfg.flag_max_target_dist = float(kw.pop("max_target_dist"))
         # ant_flagrun_env.py:17-18: exactly one of max_targets / max_target_dist drives the goals

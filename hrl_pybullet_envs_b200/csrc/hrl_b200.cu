@@ -79,6 +79,24 @@ static int cuda_fail(cudaError_t e, const char* where) {
     if (_e != cudaSuccess) return cuda_fail(_e, #call); \
   } while (0)
 
+// Every entry point runs on the handle's device and puts the caller's current device back on return (a process that
+// drives several GPUs, or PyTorch's own notion of the current device, must not be disturbed by a step on cuda:1).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); cur = -1; }
+    if (cur != dev) { err = cudaSetDevice(dev); prev = cur; }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define ON_DEVICE(dev)                                             \
+  DeviceGuard _guard(dev);                                         \
+  if (_guard.err != cudaSuccess) return cuda_fail(_guard.err, "cudaSetDevice")
+
 // ------------------------------------------------------------------------------------------
 // task-layer helpers
 // ------------------------------------------------------------------------------------------
@@ -86,11 +104,12 @@ __device__ __forceinline__ float clip5(float x) { return fminf(fmaxf(x, -5.f), 5
 
 // Flagrun goal j of episode ep: ant_flagrun_env.py:71-78; the stream is shared by all envs (:39)
 // rarely executed: kept out of line so that the hot task-layer code stays compact in the I-cache
-__device__ __noinline__ void flag_goal(const hrl_config& cfg, int ep, int j, float& gx, float& gy) {
+// `gen` counts the create_targets() calls of the env (ant_flagrun_env.py:91-96 draws fresh goals from the stream each time)
+__device__ __noinline__ void flag_goal(const hrl_config& cfg, int ep, int j, int gen, float& gx, float& gy) {
   const float half = cfg.flag_size * 0.5f;
   for (uint32_t attempt = 0;; attempt++) {
     float u[4];
-    rng_u4(cfg.flag_seed, 0u, STREAM_FLAG, attempt, (uint32_t)(ep * 128 + j), u);
+    rng_u4(cfg.flag_seed, (uint32_t)gen, STREAM_FLAG, attempt, (uint32_t)(ep * 128 + j), u);
     gx = -half + 2.f * half * u[0]; gy = -half + 2.f * half * u[1];
     if (sqrtf(gx * gx + gy * gy) < 0.5f && attempt + 1 < HRL_MAX_PLACE_ATTEMPTS) continue;
     return;
@@ -103,12 +122,17 @@ __device__ __noinline__ void flag_close_target(const hrl_config& cfg, uint32_t g
                                                float py, float& gx, float& gy) {
   const float wb = cfg.flag_size * 0.5f, lo = cfg.tol, hi = cfg.flag_max_target_dist * 0.5f;
   float g0 = wb + 1.f, g1 = wb + 1.f;
-  for (uint32_t attempt = 0; attempt < HRL_MAX_PLACE_ATTEMPTS; attempt++) {
+  bool inside = false;
+  for (uint32_t attempt = 0; attempt < HRL_MAX_CLOSE_ATTEMPTS && !inside; attempt++) {
     float u[4];
     rng_u4(cfg.flag_seed, genv, STREAM_FLAG_CLOSE, (uint32_t)steps_total, attempt * 2 + (at_reset ? 1u : 0u), u);
     g0 = (lo + (hi - lo) * u[0]) * (u[2] < 0.5f ? -1.f : 1.f) + px;
     g1 = (lo + (hi - lo) * u[1]) * (u[3] < 0.5f ? -1.f : 1.f) + py;
-    if (-wb < g0 && g0 < wb && -wb < g1 && g1 < wb) break;
+    inside = -wb < g0 && g0 < wb && -wb < g1 && g1 < wb;
+  }
+  if (!inside) {  // the reference redraws for ever; after 64 rejected draws the goal is pulled inside the world instead
+    const float lim = wb - 1e-3f;
+    g0 = fminf(fmaxf(g0, -lim), lim); g1 = fminf(fmaxf(g1, -lim), lim);
   }
   gx = g0; gy = g1;
 }
@@ -133,7 +157,7 @@ struct TaskRegs {  // replicated per-env task state held in registers
   float initial_z, potential, wtd, tx, ty;
   float ret, ret_sum;  // episode-return accumulators (HRL_SF_RETURN, HRL_SF_RETURN_SUM)
   float feet[4];
-  int t, episode, steps_total, goals_left, since, rewarded;
+  int t, episode, steps_total, goals_left, since, rewarded, gen;
 };
 
 // Flagrun next_target() (ant_flagrun_env.py:112-120): pop the next pre-drawn goal, or draw a close one
@@ -145,7 +169,7 @@ __device__ __forceinline__ bool flag_next(const hrl_config& cfg, uint32_t genv, 
   else {
     if (T.goals_left <= 0) return false;
     T.goals_left--;
-    flag_goal(cfg, T.episode - 1, T.goals_left, gx, gy);
+    flag_goal(cfg, T.episode - 1, T.goals_left, T.gen, gx, gy);
   }
   T.tx = gx; T.ty = gy;
   T.rewarded = 0;
@@ -201,7 +225,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
     s.q1 = lg.x; s.q2 = lg.y; s.qd1 = lg.z; s.qd2 = lg.w;
     T.tx = m0.x; T.ty = m0.y; T.ret = m0.z; T.ret_sum = m0.w;
     T.feet[0] = m1.x; T.feet[1] = m1.y; T.feet[2] = m1.z; T.feet[3] = m1.w;
-    T.t = i0.x; T.episode = i0.y; T.steps_total = i0.z; T.goals_left = i0.w; T.since = i1.x; T.rewarded = i1.y;
+    T.t = i0.x; T.episode = i0.y; T.steps_total = i0.z; T.goals_left = i0.w; T.since = i1.x; T.rewarded = i1.y; T.gen = i1.z;
   }
   float it_x[4], it_y[4];
   if (FAMILY == 0) {
@@ -269,12 +293,13 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
   bool first = (mode == 0);       // first compose of a full step carries the reward logic
   bool set_pot = false;           // potential <- -wtd/dt when the obs is committed (walker reset)
   int done = 0;
+  bool pend_reset = false;
   if (mode == 2) {
     const bool m = mask ? (mask[e] != 0) : true;
     todo = m ? 3 : 0;  // 3: reset request
   }
 
-  for (int guard = 0; guard < 5; guard++) {
+  for (int guard = 0; guard < 6; guard++) {
     // reset requests are executed first (register state only)
     if (todo == 3) {
       T.t = 0; T.ret = 0.f;
@@ -578,7 +603,8 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
         if (active && k == 0) {
           rew_out[e] = rew;
           done_out[e] = (uint8_t)done;
-          if (info_out) reinterpret_cast<float4*>(info_out)[e] = make_float4(inner, info1, trunc, (float)T.t);
+          // info[2]: bit 0 = TimeLimit.truncated, bit 1 = the walk target changed in this step (info['target'] is set)
+          if (info_out) reinterpret_cast<float4*>(info_out)[e] = make_float4(inner, info1, trunc + 2.f * (float)next, (float)T.t);
         }
         switched = next;
       }
@@ -587,9 +613,11 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
     int next_todo = 0;
     if (todo == 2) next_todo = 1;
     if (first && todo == 1) {
-      if (switched) next_todo = 1;  // fresh calc_state with the new target (ant_flagrun_env.py:120,190)
-      if (done && cfg.auto_reset) next_todo = 3;
-    }
+      if (switched) {  // fresh calc_state with the new target (ant_flagrun_env.py:120,190); a reset waits for it, so
+        next_todo = 1; // that the terminal observation is the one the reference returns with done
+        pend_reset = done && cfg.auto_reset;
+      } else if (done && cfg.auto_reset) next_todo = 3;
+    } else if (todo == 1 && pend_reset) { next_todo = 3; pend_reset = false; }
     const unsigned need_mask = __ballot_sync(HRL_FULL_MASK, next_todo == 3);
     if (need_mask && term_out) {
       __syncwarp();
@@ -613,7 +641,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       st.miscf[e * 2 + 0] = make_float4(T.tx, T.ty, T.ret, T.ret_sum);
       st.miscf[e * 2 + 1] = make_float4(T.feet[0], T.feet[1], T.feet[2], T.feet[3]);
       st.misci[e * 2 + 0] = make_int4(T.t, T.episode, T.steps_total, T.goals_left);
-      st.misci[e * 2 + 1] = make_int4(T.since, T.rewarded, 0, 0);
+      st.misci[e * 2 + 1] = make_int4(T.since, T.rewarded, T.gen, 0);
     }
     st.leg[e * 4 + k] = make_float4(s.q1, s.q2, s.qd1, s.qd2);
     if (FAMILY == 0) {
@@ -883,7 +911,7 @@ __global__ void get_state_kernel(int N, DevState st, float* __restrict__ f, int3
   int32_t* q = iv + (size_t)e * HRL_STATE_I;
   for (int i = 0; i < HRL_STATE_I; i++) q[i] = 0;
   q[HRL_SI_T] = i0.x; q[HRL_SI_EPISODE] = i0.y; q[HRL_SI_STEPS] = i0.z; q[HRL_SI_GOALS_LEFT] = i0.w;
-  q[HRL_SI_SINCE] = i1.x; q[HRL_SI_REWARDED] = i1.y;
+  q[HRL_SI_SINCE] = i1.x; q[HRL_SI_REWARDED] = i1.y; q[HRL_SI_GOAL_GEN] = i1.z;
 }
 
 __global__ void set_state_kernel(int N, DevState st, const float* __restrict__ f, const int32_t* __restrict__ iv) {
@@ -902,7 +930,7 @@ __global__ void set_state_kernel(int N, DevState st, const float* __restrict__ f
     st.items[e * 8 + l] = make_float4(o[HRL_SF_ITEMS + 4 * l], o[HRL_SF_ITEMS + 4 * l + 1], o[HRL_SF_ITEMS + 4 * l + 2], o[HRL_SF_ITEMS + 4 * l + 3]);
   const int32_t* q = iv + (size_t)e * HRL_STATE_I;
   st.misci[e * 2] = make_int4(q[HRL_SI_T], q[HRL_SI_EPISODE], q[HRL_SI_STEPS], q[HRL_SI_GOALS_LEFT]);
-  st.misci[e * 2 + 1] = make_int4(q[HRL_SI_SINCE], q[HRL_SI_REWARDED], 0, 0);
+  st.misci[e * 2 + 1] = make_int4(q[HRL_SI_SINCE], q[HRL_SI_REWARDED], q[HRL_SI_GOAL_GEN], 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1080,7 +1108,7 @@ static int validate(const hrl_config* c) {
 
 int hrl_destroy(hrl_handle* h) {
   if (!h) return HRL_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   cudaFree(h->st.base); cudaFree(h->st.leg); cudaFree(h->st.items); cudaFree(h->st.miscf); cudaFree(h->st.misci);
   cudaFree(h->st.stats); cudaFree(h->d_bounds); cudaFree(h->st.fin_count);
   if (h->h_flag) cudaFreeHost(h->h_flag);
@@ -1098,7 +1126,7 @@ int hrl_create(const hrl_config* cfg, int32_t device, hrl_handle** out) {
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0) return set_err(HRL_E_CUDA, "no CUDA device: this library has no CPU fallback");
   if (device < 0 || device >= ndev) return set_err(HRL_E_INVALID, "bad device index");
-  CK(cudaSetDevice(device));
+  ON_DEVICE(device);
   hrl_handle* h = new hrl_handle();
   memset(h, 0, sizeof *h);
   h->cfg = *cfg; h->device = device; h->N = cfg->num_envs; h->D = hrl_obs_dim(cfg); h->A = hrl_act_dim(cfg);
@@ -1130,26 +1158,33 @@ int hrl_create(const hrl_config* cfg, int32_t device, hrl_handle** out) {
     h->s_out_bytes = total;
   }
 #undef ALLOC
+  // late failures release the handle; *out is assigned last
+#define CKH(call)                                                               \
+  do {                                                                          \
+    cudaError_t _e = (call);                                                    \
+    if (_e != cudaSuccess) { hrl_destroy(h); return cuda_fail(_e, #call); }     \
+  } while (0)
   float b[28];
   h->n_lines = scene_bounds(cfg, b);
-  CK(cudaMemcpy(h->d_bounds, b, sizeof b, cudaMemcpyHostToDevice));
+  CKH(cudaMemcpy(h->d_bounds, b, sizeof b, cudaMemcpyHostToDevice));
   // opt in to the dynamic shared memory the ant kernels need
   const int smem = HRL_WARPS_PER_CTA * SMEM_PER_WARP_FLOATS * (int)sizeof(float);
-  CK(cudaFuncSetAttribute(ant_env_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CK(cudaFuncSetAttribute(ant_env_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CKH(cudaFuncSetAttribute(ant_env_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CKH(cudaFuncSetAttribute(ant_env_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   // the kernels live in shared memory and registers (hardly any L1 traffic): take the whole carve-out, 6 CTAs / SM
-  CK(cudaFuncSetAttribute(ant_env_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(ant_env_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  *out = h;
+  CKH(cudaFuncSetAttribute(ant_env_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CKH(cudaFuncSetAttribute(ant_env_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   // like the reference, reset() must be called before the first step(); an un-reset env has a
   // zero quaternion, produces a non-finite observation and is ended by the NaN guard
-  CK(cudaDeviceSynchronize());
+  CKH(cudaDeviceSynchronize());
+#undef CKH
+  *out = h;
   return HRL_OK;
 }
 
 static int launch_env(hrl_handle* h, int mode, int n_sub, const float* act, const uint8_t* mask, float* obs, float* rew,
                       uint8_t* done, float* info, float* term, cudaStream_t s, bool signal = false) {
-  CK(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   DevState st = h->st;
   st.fin_flag = nullptr;
   if (signal && h->h_flag && h->cfg.env_kind != HRL_POINT_GATHER) {
@@ -1228,7 +1263,7 @@ int hrl_step_host(hrl_handle* h, const float* h_actions, float* h_obs, float* h_
                   void* stream) {
   if (!h || !h_actions || !h_obs || !h_rew || !h_done) return set_err(HRL_E_INVALID, "null argument to hrl_step_host");
   cudaStream_t s = (cudaStream_t)stream;
-  CK(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   const size_t N = (size_t)h->N;
   // inputs: pinned actions are read by the kernel in place; anything else is copied H2D first
   const float* d_act = nullptr;
@@ -1282,7 +1317,7 @@ __global__ void flag_next_kernel(const __grid_constant__ hrl_config cfg, DevStat
   int4 i0 = st.misci[e * 2 + 0], i1 = st.misci[e * 2 + 1];
   TaskRegs T;
   T.initial_z = b0.w; T.potential = b2.w; T.wtd = b3.w; T.tx = m0.x; T.ty = m0.y; T.ret = m0.z; T.ret_sum = m0.w;
-  T.t = i0.x; T.episode = i0.y; T.steps_total = i0.z; T.goals_left = i0.w; T.since = i1.x; T.rewarded = i1.y;
+  T.t = i0.x; T.episode = i0.y; T.steps_total = i0.z; T.goals_left = i0.w; T.since = i1.x; T.rewarded = i1.y; T.gen = i1.z;
   if (!flag_next(cfg, (uint32_t)(cfg.env_index_offset + e), T, b0.x, b0.y, 0)) return;
   st.base[e * 4 + 2] = make_float4(b2.x, b2.y, b2.z, T.potential);
   st.miscf[e * 2 + 0] = make_float4(T.tx, T.ty, m0.z, m0.w);
@@ -1293,7 +1328,7 @@ __global__ void flag_next_kernel(const __grid_constant__ hrl_config cfg, DevStat
 int hrl_flagrun_next_target(hrl_handle* h, const uint8_t* d_mask, void* stream) {
   if (!h) return set_err(HRL_E_INVALID, "null handle");
   if (h->cfg.env_kind != HRL_ANT_FLAGRUN) return set_err(HRL_E_INVALID, "hrl_flagrun_next_target: not an AntFlagrun handle");
-  CK(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   flag_next_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->cfg, h->st, d_mask);
   g_launches++;
   CK(cudaGetLastError());
@@ -1312,7 +1347,7 @@ int hrl_substeps(hrl_handle* h, const float* d_actions, int32_t n_sub, void* str
 
 int hrl_get_state(hrl_handle* h, float* d_f, int32_t* d_i, void* stream) {
   if (!h || !d_f || !d_i) return set_err(HRL_E_INVALID, "null argument to hrl_get_state");
-  CK(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   get_state_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->N, h->st, d_f, d_i);
   g_launches++;
   CK(cudaGetLastError());
@@ -1320,7 +1355,7 @@ int hrl_get_state(hrl_handle* h, float* d_f, int32_t* d_i, void* stream) {
 }
 int hrl_set_state(hrl_handle* h, const float* d_f, const int32_t* d_i, void* stream) {
   if (!h || !d_f || !d_i) return set_err(HRL_E_INVALID, "null argument to hrl_set_state");
-  CK(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   set_state_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->N, h->st, d_f, d_i);
   g_launches++;
   CK(cudaGetLastError());
@@ -1352,10 +1387,31 @@ int hrl_sense_walls(int32_t M, int32_t n_bins, float span, float range, int32_t 
   return HRL_OK;
 }
 
+// Measurement aid: everything enqueued on `stream` after this call waits on the device until the 32-bit word at
+// d_flag (pinned host memory the device can address, or device memory) equals `expect`, or `timeout_ns` elapses.
+// bench.py queues a whole batch of (L2 flush, event, step, event) behind one gate and then opens it, so that the
+// per-step event pairs never contain a host-side launch gap.
+__global__ void gate_kernel(const volatile unsigned int* flag, unsigned int expect, unsigned long long timeout_ns) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (*flag != expect) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > timeout_ns) break;
+    __nanosleep(500);
+  }
+}
+int hrl_stream_gate(const uint32_t* d_flag, uint32_t expect, uint64_t timeout_ns, void* stream) {
+  if (!d_flag) return set_err(HRL_E_INVALID, "null flag for hrl_stream_gate");
+  gate_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_flag, expect, (unsigned long long)timeout_ns);
+  g_launches++;
+  CK(cudaGetLastError());
+  return HRL_OK;
+}
+
 /* instrumentation for the FLOP model (bench.py roofline): contacts, limit rows, env-substeps */
 int hrl_get_stats(hrl_handle* h, unsigned long long out[4], int reset) {
   if (!h || !out) return set_err(HRL_E_INVALID, "null argument to hrl_get_stats");
-  CK(cudaSetDevice(h->device));
+  ON_DEVICE(h->device);
   CK(cudaMemcpy(out, h->st.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   if (reset) CK(cudaMemset(h->st.stats, 0, 4 * sizeof(unsigned long long)));
   return HRL_OK;

@@ -72,6 +72,7 @@ constexpr float HALF = 0.35f;
 // ---- Philox4x32-10, same addressing as oracle/hrl_oracle.c -----------------------------------
 enum { STREAM_JOINT = 0, STREAM_ITEM = 1, STREAM_GOAL = 2, STREAM_FLAG = 3, STREAM_ITEM_RESET = 4, STREAM_FLAG_CLOSE = 5 };
 #define HRL_MAX_PLACE_ATTEMPTS 16
+#define HRL_MAX_CLOSE_ATTEMPTS 64  // create_close_target near a corner rejects ~3 of 4 draws
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                                uint32_t k1, uint32_t out[4]) {
 #pragma unroll

@@ -40,20 +40,24 @@ class SingleEnv:
 
     metadata = {"render.modes": []}
 
-    def __init__(self, env_id, device=0, seed=0, **kwargs):
+    def __init__(self, env_id, device=0, seed=None, **kwargs):
         from .vec_env import VecEnv
         self.vec = VecEnv(env_id, 1, device=device, seed=seed, auto_reset=False, **kwargs)
         self.observation_space = Box(-np.inf, np.inf, (self.vec.D,))
         self.action_space = Box(-1.0, 1.0, (self.vec.A,))
         self.spec = type("Spec", (), {"id": env_id, "max_episode_steps": 2000})()
+        self._ctor_seed = seed   # the ctor kwarg (for Flagrun: the shared goal stream, ant_flagrun_env.py:16,39)
         self._seed = seed
         self._kwargs = kwargs
 
     def seed(self, seed=None):
+        """gym's env.seed(s): re-keys the env's own RNG streams (joint noise, item placement, maze goal); the Flagrun
+        goal stream keeps the ctor's seed, like the reference's private RandomState."""
         if seed is not None and seed != self._seed:
             from .vec_env import VecEnv
             self.vec.close()
-            self.vec = VecEnv(self.spec.id, 1, device=self.vec.device.index, seed=seed, auto_reset=False, **self._kwargs)
+            self.vec = VecEnv(self.spec.id, 1, device=self.vec.device.index, seed=self._ctor_seed, env_seed=seed, auto_reset=False,
+                              **self._kwargs)
             self._seed = seed
         return [self._seed]
 
@@ -70,8 +74,12 @@ class SingleEnv:
             if k == "TimeLimit.truncated":
                 if bool(v[0]):
                     i[k] = True
+            elif k == "target_switched":
+                if bool(v[0]):   # ant_flagrun_env.py:188-191,199: info['target'] only in a step that switched goals
+                    t = info["target"]
+                    i["target"] = (float(t[0, 0]), float(t[0, 1]))
             elif k == "target":
-                i[k] = (float(v[0, 0]), float(v[0, 1]))
+                pass
             elif k != "terminal_obs":
                 i[k] = float(v[0])
         return obs[0].copy(), float(rew[0]), bool(done[0]), i
@@ -131,3 +139,6 @@ def register_with_installed_gym():
         except ImportError:
             pass
     return done
+
+
+REGISTERED_WITH = register_with_installed_gym()   # [] in this image (no gym / gymnasium installed)

@@ -31,5 +31,13 @@ def flop_per_env_step(contacts, limit_rows, substeps=4, iters=5):
     return substeps * per_sub + TASK_FLOP_PER_STEP
 
 
+def bytes_per_env_step(kind, obs_dim, act_dim):
+    """Algorithmic HBM bytes per env-step: robot state 29 f32 read + written (232), the 16 item
+    positions read (128, Gather envs only), counters / accumulators 24, the action read, the observation written,
+    reward + done 5.  AntGather: 232 + 128 + 24 + 32 + 184 + 5 = 605."""
+    items = 128 if kind in (0, 4) else 0   # HRL_ANT_GATHER, HRL_POINT_GATHER
+    return 232 + items + 24 + 4 * act_dim + 4 * obs_dim + 5
+
+
 def fp32_peak_tflops(sm_mhz):
     return N_SM * FP32_LANES_PER_SM * 2 * sm_mhz * 1e6 / 1e12

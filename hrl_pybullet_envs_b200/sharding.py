@@ -29,3 +29,14 @@ def sum_episode_stats(episodes, steps, extra=(), device=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return [float(x) for x in t.cpu()]
+
+
+def gather_over_ranks(values, device=None):
+    """Every rank's list of floats, as a list indexed by rank (per-rank timing reports of the benchmark)."""
+    import torch.distributed as dist
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+        dist.all_gather(out, t)
+        return [[float(x) for x in o.cpu()] for o in out]
+    return [[float(x) for x in t.cpu()]]

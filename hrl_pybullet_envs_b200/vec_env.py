@@ -10,7 +10,12 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .config import (ENV_IDS, HRL_STATE_F, HRL_STATE_I, HRL_ANT_FLAGRUN, HRL_ANT_GATHER, HRL_POINT_GATHER, SF_TARGET, SI_GOALS_LEFT, apply_kwargs)
+import os
+
+from .config import (ENV_IDS, HRL_STATE_F, HRL_STATE_I, HRL_ANT_FLAGRUN, HRL_ANT_GATHER, HRL_POINT_GATHER, HrlConfig, SF_TARGET, SI_GOALS_LEFT,
+                     SI_GOAL_GEN, apply_kwargs)
+
+_NVTX = bool(int(os.environ.get("HRL_NVTX", "0")))   # NVTX ranges around reset / step, off by default
 
 
 def _ptr(t):
@@ -29,9 +34,11 @@ class LazyInfo(Mapping):
         keys = ["TimeLimit.truncated", "episode_length"]
         keys += ["food_rew", "dead_rew"] if kind in (HRL_ANT_GATHER, HRL_POINT_GATHER) else ["inner_rew"]
         if kind == HRL_ANT_FLAGRUN:
-            keys.append("goals_left")
+            # ant_flagrun_env.py:188-191,199: the reference sets i['target'] = self.goal only in a step that switched goals;
+            # 'target_switched' is that condition per env, 'target' the current goal of every env (read on access)
+            keys += ["goals_left", "target_switched"]
             if env is not None:
-                keys.append("target")   # ant_flagrun_env.py:188,199: i['target'] = self.goal (here: the current goal of every env)
+                keys.append("target")
         if term is not None:
             keys.append("terminal_obs")
         self._keys = keys
@@ -40,8 +47,10 @@ class LazyInfo(Mapping):
         if k not in self._keys:
             raise KeyError(k)
         r = self.raw
-        if k == "TimeLimit.truncated":
-            return r[:, 2] > 0
+        if k == "TimeLimit.truncated":   # info[:, 2] holds flag bits: 1 = truncated, 2 = Flagrun goal switched
+            return (r[:, 2] % 2) > 0
+        if k == "target_switched":
+            return r[:, 2] >= 2
         if k == "episode_length":
             return r[:, 3]
         if k in ("food_rew", "inner_rew"):
@@ -85,8 +94,12 @@ class VecEnv:
     ``seed`` and ``env_index_offset`` (global index of env 0, for multi-GPU shards).
     """
 
-    def __init__(self, env_id, num_envs, device=0, seed=0, env_index_offset=0, auto_reset=True,
-                 max_episode_steps=2000, config_overrides=None, **kwargs):
+    def __init__(self, env_id, num_envs, device=0, seed=None, env_index_offset=0, auto_reset=True,
+                 max_episode_steps=2000, config_overrides=None, env_seed=None, **kwargs):
+        """``seed`` keys the per-env RNG streams (joint noise, item placement, maze goal choice: what ``env.seed(s)``
+        and the Maze ctor's ``seed`` kwarg feed in the reference, ant_maze_bullet_env.py:48,99-102).  For
+        AntFlagrunBulletEnv an explicit ``seed`` is ALSO the ctor kwarg of the reference (ant_flagrun_env.py:16,39): it
+        seeds the goal stream shared by all envs (default 123).  ``env_seed`` overrides the per-env key alone."""
         if env_id not in ENV_IDS:
             raise KeyError("unknown env id %r; known: %s" % (env_id, sorted(ENV_IDS)))
         if not torch.cuda.is_available():
@@ -96,14 +109,18 @@ class VecEnv:
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
         cfg = _cabi.default_config(self.kind, num_envs)
         apply_kwargs(cfg, self.kind, kwargs)
-        if self.kind not in (HRL_ANT_FLAGRUN,) and "seed" not in kwargs:
-            cfg.seed = int(seed)
-        elif self.kind == HRL_ANT_FLAGRUN:
-            cfg.seed = int(seed)  # Flagrun's `seed` kwarg feeds the shared goal stream (flag_seed)
+        cfg.seed = int(seed or 0)
+        if self.kind == HRL_ANT_FLAGRUN and seed is not None:
+            cfg.flag_seed = int(seed)
+        if env_seed is not None:
+            cfg.seed = int(env_seed)
         cfg.env_index_offset = int(env_index_offset)
         cfg.auto_reset = int(bool(auto_reset))
         cfg.max_episode_steps = int(max_episode_steps)
+        known = {f[0] for f in HrlConfig._fields_}
         for k, v in (config_overrides or {}).items():
+            if k not in known:
+                raise KeyError("config_overrides: hrl_config has no field %r" % k)
             setattr(cfg, k, v)
         self.cfg = cfg
         self.L = _cabi.lib()
@@ -140,11 +157,25 @@ class VecEnv:
         """Re-seeding happens at construction (counter RNG keyed by (seed, env index))."""
         return [self.cfg.seed]
 
+    def _mask(self, mask):
+        if mask is None:
+            return None
+        m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        if m.numel() != self.N:
+            raise ValueError("mask must have %d entries, got %d" % (self.N, m.numel()))
+        return m
+
     def reset(self, mask=None):
-        m = None
-        if mask is not None:
-            m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        """Reset all envs (or the masked ones) and return obs[N, D]; rows of envs outside the mask hold the observation
+        of their CURRENT state (refreshed, so the returned tensor is always a consistent batch)."""
+        m = self._mask(mask)
+        if _NVTX:
+            torch.cuda.nvtx.range_push("hrl.reset")
+        if m is not None:
+            _cabi.check(self.L.hrl_observe(self.h, _ptr(self._obs), self._stream()))
         _cabi.check(self.L.hrl_reset(self.h, _ptr(m), _ptr(self._obs), self._stream()))
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
         return self._obs
 
     def step(self, actions, want_terminal_obs=False, out=None):
@@ -156,8 +187,8 @@ class VecEnv:
         a = actions
         if a.dtype != torch.float32 or not a.is_contiguous() or a.device != self.device:
             a = a.to(device=self.device, dtype=torch.float32).contiguous()
-        if a.numel() != self.N * self.A:
-            raise ValueError("actions must have shape (%d, %d)" % (self.N, self.A))
+        if tuple(a.shape) != (self.N, self.A):
+            raise ValueError("actions must have shape (%d, %d), got %s" % (self.N, self.A, tuple(a.shape)))
         term = None
         if want_terminal_obs:
             if self._term is None:
@@ -171,9 +202,33 @@ class VecEnv:
                 if tuple(t.shape) != shape or t.dtype not in dts or not t.is_contiguous() or t.device != self.device:
                     raise ValueError("out tensors must be contiguous CUDA tensors obs[%d,%d] f32, rew[%d] f32, done[%d] u8/bool"
                                      % (self.N, self.D, self.N, self.N))
+        if _NVTX:
+            torch.cuda.nvtx.range_push("hrl.step")
         _cabi.check(self.L.hrl_step(self.h, _ptr(a), _ptr(obs), _ptr(rew), _ptr(done),
                                     _ptr(self._info), _ptr(term), self._stream()))
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
         return obs, rew, done.view(torch.bool), self._info_dict(self._info, term)
+
+    def capture_rollout(self, actions, buf=None):
+        """CUDA-graph launch: capture ``T = actions.shape[0]`` consecutive steps, step t
+        reading ``actions[t]`` (a [T, N, A] CUDA tensor the caller refills between replays) and writing slot t of
+        ``buf`` (a ``RolloutBuffer``; created when None).  Returns ``(graph, buf)``; ``graph.replay()`` runs the T
+        steps with ONE launch from the host.  ``step()`` itself is capture-safe (no allocation, no synchronisation),
+        so a caller can equally capture its own policy + ``env.step`` loop with ``torch.cuda.graph``."""
+        a = actions
+        if a.dtype != torch.float32 or not a.is_contiguous() or a.device != self.device or tuple(a.shape[1:]) != (self.N, self.A):
+            raise ValueError("actions must be a contiguous float32 CUDA tensor [T, %d, %d]" % (self.N, self.A))
+        T = a.shape[0]
+        buf = buf or RolloutBuffer(self, T)
+        if buf.T < T:
+            raise ValueError("rollout buffer holds %d steps, need %d" % (buf.T, T))
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for t in range(T):
+                self.step(a[t], out=buf.slot(t))
+        return g, buf
 
     def rollout_buffer(self, horizon):
         """Device-resident storage for ``horizon`` steps; ``step(a, out=buf.slot(t))`` fills slot t in place."""
@@ -219,7 +274,9 @@ class VecEnv:
         if self._host is None:
             self._host = self._host_buffers()
         H = self._host
-        if isinstance(actions, np.ndarray) and actions.dtype == np.float32 and actions.flags.c_contiguous and actions.size == self.N * self.A:
+        if np.size(actions) != self.N * self.A:
+            raise ValueError("actions must have shape (%d, %d)" % (self.N, self.A))
+        if isinstance(actions, np.ndarray) and actions.dtype == np.float32 and actions.flags.c_contiguous:
             p_act = C.c_void_p(actions.ctypes.data)   # used in place: read over PCIe when pinned, copied H2D by the library when not
         else:
             np.copyto(H["act_np"], np.asarray(actions).reshape(self.N, self.A), casting="same_kind")
@@ -271,12 +328,13 @@ class VecEnv:
             raise ValueError("n must be in [0, 127]")
         f, i = self.get_state()
         i[:, SI_GOALS_LEFT] = n
+        i[:, SI_GOAL_GEN] += 1     # every call draws fresh goals from the shared stream, like the reference
         self.set_state(f, i)
 
     def next_target(self, mask=None):
         """next_target() (ant_flagrun_env.py:112-120) for all envs or the masked ones; returns the fresh observation."""
         self._flagrun_only()
-        m = None if mask is None else torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        m = self._mask(mask)
         _cabi.check(self.L.hrl_flagrun_next_target(self.h, _ptr(m), self._stream()))
         return self.observe()
 

@@ -69,7 +69,8 @@ enum {
   HRL_SI_STEPS = 2,      /* steps taken since creation (RNG draw index of respawns)  */
   HRL_SI_GOALS_LEFT = 3, /* Flagrun: goals still in the list                         */
   HRL_SI_SINCE = 4,      /* Flagrun: steps_since_goal_change (survives reset)        */
-  HRL_SI_REWARDED = 5    /* Flagrun: _rewarded; 6,7 spare                            */
+  HRL_SI_REWARDED = 5,   /* Flagrun: _rewarded                                       */
+  HRL_SI_GOAL_GEN = 6    /* Flagrun: create_targets() calls so far (each draws fresh goals, ant_flagrun_env.py:91-96); 7 spare */
 };
 
 /* ---- configuration: the reference's ctor kwargs + the recalled third-party constants --- */
@@ -163,7 +164,9 @@ int hrl_reset(hrl_handle* h, const uint8_t* d_mask, float* d_obs, void* stream);
 /* Replaces env.step(a) (ant_gather_env.py:76-119, ant_maze_bullet_env.py:77-97,
  * ant_flagrun_env.py:162-204, MjAnt.py:36-97, gather_base.py:74-109) for all N envs.
  *   d_actions f32[N, act_dim]; d_obs f32[N, obs_dim]; d_rew f32[N]; d_done u8[N];
- *   d_info    f32[N, 4] or NULL: (food_rew | inner reward, dead_rew, TimeLimit.truncated, episode length)
+ *   d_info    f32[N, 4] or NULL: (food_rew | inner reward, dead_rew | goals_left, flags, episode length);
+ *             flags: bit 0 = TimeLimit.truncated, bit 1 (Flagrun) = the walk target changed in this step, i.e. the
+ *             reference sets info['target'] (ant_flagrun_env.py:188-191,199)
  *   d_terminal_obs f32[N, obs_dim] or NULL: pre-reset observation of envs that finished. */
 int hrl_step(hrl_handle* h, const float* d_actions, float* d_obs, float* d_rew, uint8_t* d_done,
              float* d_info, float* d_terminal_obs, void* stream);
@@ -222,6 +225,16 @@ int hrl_sense_walls(int32_t M, int32_t n_bins, float span, float range, int32_t 
 /* `n_sub` physics sub-steps on the handle's current state (no task logic, no reset):
  * replaces scene.global_step() -> p.stepSimulation() (ant_gather_env.py:78). */
 int hrl_substeps(hrl_handle* h, const float* d_actions, int32_t n_sub, void* stream);
+
+/* In-kernel counters feeding the FLOP model of bench.py (SURVEY.md section 5 "in-kernel optional counters"):
+ * out = {contacts, joint-limit rows, env-substeps, reserved} accumulated since the last reset; synchronises. */
+int hrl_get_stats(hrl_handle* h, unsigned long long out[4], int reset);
+
+/* Measurement aid (bench.py): work enqueued on `stream` after this call waits ON THE DEVICE until the 32-bit word at
+ * d_flag (pinned host memory the device can address, or device memory) equals `expect`, or `timeout_ns` elapsed.
+ * Lets a caller queue a batch of steps with their timing events and release them at once, so that no host-side
+ * launch gap can fall between an event pair.  Not part of the reference's surface. */
+int hrl_stream_gate(const uint32_t* d_flag, uint32_t expect, uint64_t timeout_ns, void* stream);
 
 /* Number of kernels this library has launched since load (bench's gpu_launches claim). */
 int64_t hrl_launch_count(void);

@@ -77,6 +77,7 @@ static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
  *   flagrun goal j   : stream FLAG (key flag_seed, env 0), draw = attempt, sub = episode*128 + j */
 enum { STREAM_JOINT = 0, STREAM_ITEM = 1, STREAM_GOAL = 2, STREAM_FLAG = 3, STREAM_ITEM_RESET = 4, STREAM_FLAG_CLOSE = 5 };
 #define MAX_PLACE_ATTEMPTS 16
+#define MAX_CLOSE_ATTEMPTS 64
 /* 4 uniforms in [0,1) with 24 bits each (exact in float and double) */
 static void rng_u4(uint64_t seed, uint32_t env, uint32_t stream, uint32_t draw, uint32_t sub, real u[4]) {
   uint32_t o[4];
@@ -271,7 +272,7 @@ typedef struct {
   real initial_z, potential, target[2], wtd, feet[4];
   real ret, ret_sum; /* episode-return accumulators (HRL_SF_RETURN, HRL_SF_RETURN_SUM) */
   real items[HRL_MAX_ITEMS][2];
-  int32_t t, episode, steps_total, goals_left, since, rewarded;
+  int32_t t, episode, steps_total, goals_left, since, rewarded, goal_gen;
 } env_state;
 
 struct hrlo_env {
@@ -1132,10 +1133,10 @@ static void place_items(hrlo_env* E, int e, env_state* s) {
 }
 
 /* Flagrun goal j of episode ep: ant_flagrun_env.py:71-78, stream shared by all envs (:39). */
-static void flag_goal(const hrl_config* cfg, int episode, int j, real g[2]) {
+static void flag_goal(const hrl_config* cfg, int episode, int j, int gen, real g[2]) {
   for (uint32_t attempt = 0;; attempt++) {
-    real u[4];
-    rng_u4(cfg->flag_seed, 0, STREAM_FLAG, attempt, (uint32_t)(episode * 128 + j), u);
+    real u[4]; /* gen = create_targets() calls so far: each call draws fresh goals from the stream (:91-96) */
+    rng_u4(cfg->flag_seed, (uint32_t)gen, STREAM_FLAG, attempt, (uint32_t)(episode * 128 + j), u);
     real half = (real)cfg->flag_size / 2;
     g[0] = -half + 2 * half * u[0]; g[1] = -half + 2 * half * u[1];
     if (R_SQRT(g[0] * g[0] + g[1] * g[1]) < (real)0.5 && attempt + 1 < MAX_PLACE_ATTEMPTS) continue;
@@ -1249,21 +1250,26 @@ static int flag_next_target(hrlo_env* E, int e, env_state* s, int ep, calc_t* c,
     /* create_close_target (ant_flagrun_env.py:80-89): offset of magnitude U(tol, max_target_dist/2) per
      * axis with a random sign around the true torso xy, redrawn until strictly inside the world */
     real wb = (real)cfg->flag_size / 2, g0 = wb + 1, g1 = wb + 1;
-    for (uint32_t attempt = 0; attempt < MAX_PLACE_ATTEMPTS; attempt++) {
+    int inside = 0;
+    for (uint32_t attempt = 0; attempt < MAX_CLOSE_ATTEMPTS && !inside; attempt++) {
       real u[4];
       rng_u4(cfg->flag_seed, (uint32_t)(cfg->env_index_offset + e), STREAM_FLAG_CLOSE, (uint32_t)s->steps_total,
              attempt * 2 + (uint32_t)(at_reset != 0), u);
       real lo = (real)cfg->tol, hi = (real)cfg->flag_max_target_dist / 2;
       g0 = (lo + (hi - lo) * u[0]) * (u[2] < (real)0.5 ? -1 : 1) + s->pos[0];
       g1 = (lo + (hi - lo) * u[1]) * (u[3] < (real)0.5 ? -1 : 1) + s->pos[1];
-      if (-wb < g0 && g0 < wb && -wb < g1 && g1 < wb) break;
+      inside = -wb < g0 && g0 < wb && -wb < g1 && g1 < wb;
+    }
+    if (!inside) { /* the reference redraws for ever; after 64 rejected draws the goal is pulled inside the world */
+      real lim = wb - (real)1e-3f;
+      g0 = g0 < -lim ? -lim : (g0 > lim ? lim : g0); g1 = g1 < -lim ? -lim : (g1 > lim ? lim : g1);
     }
     s->target[0] = g0; s->target[1] = g1;
   } else {
     if (s->goals_left <= 0) return 0; /* goals.pop() raises IndexError */
     s->goals_left--;
     if (E->replay_goals) { s->target[0] = (real)E->replay_goals[2 * s->goals_left]; s->target[1] = (real)E->replay_goals[2 * s->goals_left + 1]; }
-    else flag_goal(cfg, ep, s->goals_left, s->target);
+    else flag_goal(cfg, ep, s->goals_left, s->goal_gen, s->target);
   }
   s->rewarded = 0;
   if (E->replay_stub_robot) { s->potential = -1; return 1; }
@@ -1287,19 +1293,19 @@ static int maze_task(const hrl_config* cfg, const env_state* s, real inner, int 
 }
 
 /* AntFlagrunBulletEnv.step after the inner walker step (ant_flagrun_env.py:167-202). */
-static int flagrun_task(hrlo_env* E, int e, env_state* s, calc_t* c, real inner, int done, real* rew) {
+static int flagrun_task(hrlo_env* E, int e, env_state* s, calc_t* c, real inner, int done, real* rew, int* switched) {
   const hrl_config* cfg = &E->cfg;
   real r = inner;
   s->since += 1;
   if (s->wtd < (real)cfg->tol) {
     if (!s->rewarded) { r += (real)cfg->goal_reach_rew; s->rewarded = 1; }
     if (cfg->flag_switch_on_collision) {
-      if (flag_next_target(E, e, s, s->episode - 1, c, 0)) s->since = 0;
+      if (flag_next_target(E, e, s, s->episode - 1, c, 0)) { s->since = 0; *switched = 1; }
       else done = 1; /* IndexError -> d = True (:193) */
     }
   }
   if (cfg->flag_timeout > 0 && cfg->flag_timeout <= s->since) {
-    if (flag_next_target(E, e, s, s->episode - 1, c, 0)) s->since = 0;
+    if (flag_next_target(E, e, s, s->episode - 1, c, 0)) { s->since = 0; *switched = 1; }
     else done = 1;
   }
   *rew = r;
@@ -1373,7 +1379,7 @@ int hrlo_scene_bounds(const hrl_config* cfg, double* b) {
 static int step_env(hrlo_env* E, int e, const float* act, real* obs, real* rew, real* info) {
   hrl_config* cfg = &E->cfg;
   env_state* s = &E->s[e];
-  int kind = cfg->env_kind, done = 0;
+  int kind = cfg->env_kind, done = 0, switched = 0;
   info[0] = info[1] = info[2] = info[3] = 0;
   *rew = 0;
   if (kind == HRL_POINT_GATHER) {
@@ -1432,7 +1438,7 @@ static int step_env(hrlo_env* E, int e, const float* act, real* obs, real* rew, 
         if (s->wtd < (real)cfg->tol) { *rew += 1; done = 1; }
       } else if (kind == HRL_ANT_FLAGRUN) {
         /* ant_flagrun_env.py:162-204 */
-        done = flagrun_task(E, e, s, &c, inner, done, rew);
+        done = flagrun_task(E, e, s, &c, inner, done, rew, &switched);
         compose_obs(E, s, &c, obs); /* the state after a goal switch (:120,190) + optional lidar */
         info[1] = (real)s->goals_left;
       } else {
@@ -1444,6 +1450,7 @@ static int step_env(hrlo_env* E, int e, const float* act, real* obs, real* rew, 
   s->steps_total++;
   /* gym TimeLimit */
   if (cfg->max_episode_steps > 0 && s->t >= cfg->max_episode_steps) { info[2] = done ? 0 : 1; done = 1; }
+  info[2] += 2 * switched; /* bit 1: the walk target changed in this step (info['target'], ant_flagrun_env.py:188-191,199) */
   s->ret += *rew;
   if (done) { s->ret_sum += s->ret; s->ret = 0; }
   info[3] = (real)s->t;
@@ -1600,6 +1607,7 @@ int hrlo_get_state(hrlo_env* E, real* f, int32_t* iv) {
     memset(q, 0, sizeof(int32_t) * HRL_STATE_I);
     q[HRL_SI_T] = s->t; q[HRL_SI_EPISODE] = s->episode; q[HRL_SI_STEPS] = s->steps_total;
     q[HRL_SI_GOALS_LEFT] = s->goals_left; q[HRL_SI_SINCE] = s->since; q[HRL_SI_REWARDED] = s->rewarded;
+    q[HRL_SI_GOAL_GEN] = s->goal_gen;
   }
   return HRL_OK;
 }
@@ -1617,6 +1625,7 @@ int hrlo_set_state(hrlo_env* E, const real* f, const int32_t* iv) {
     const int32_t* q = iv + (size_t)e * HRL_STATE_I;
     s->t = q[HRL_SI_T]; s->episode = q[HRL_SI_EPISODE]; s->steps_total = q[HRL_SI_STEPS];
     s->goals_left = q[HRL_SI_GOALS_LEFT]; s->since = q[HRL_SI_SINCE]; s->rewarded = q[HRL_SI_REWARDED];
+    s->goal_gen = q[HRL_SI_GOAL_GEN];
   }
   return HRL_OK;
 }
@@ -1680,7 +1689,8 @@ int hrlo_flagrun_replay(const hrl_config* cfg, const double* goals, int n_steps,
   for (; i < n_steps; i++) {
     s->wtd = (real)wtd[i];
     real r;
-    int d = flagrun_task(E, 0, s, &cs, (real)inner_r[i], 0, &r);
+    int sw = 0;
+    int d = flagrun_task(E, 0, s, &cs, (real)inner_r[i], 0, &r, &sw);
     rew[i] = r; done_out[i] = d; target[2 * i] = s->target[0]; target[2 * i + 1] = s->target[1];
     since[i] = s->since; rewarded[i] = s->rewarded;
     if (d) { i++; break; }
@@ -1730,4 +1740,4 @@ void hrlo_stats(hrlo_env* E, double out[3]) { out[0] = E->n_contacts; out[1] = E
 void hrlo_rng_u4(uint64_t seed, uint32_t env, uint32_t stream, uint32_t draw, uint32_t sub, double* u) {
   real r[4]; rng_u4(seed, env, stream, draw, sub, r); for (int i = 0; i < 4; i++) u[i] = r[i];
 }
-void hrlo_flag_goal(const hrl_config* cfg, int episode, int j, double* g) { real r[2]; flag_goal(cfg, episode, j, r); g[0] = r[0]; g[1] = r[1]; }
+void hrlo_flag_goal(const hrl_config* cfg, int episode, int j, double* g) { real r[2]; flag_goal(cfg, episode, j, 0, r); g[0] = r[0]; g[1] = r[1]; }

@@ -108,9 +108,16 @@ class OracleVecEnv:
         self.threads = max(1, int(threads))
 
     @classmethod
-    def make(cls, env_id, num_envs, seed=0, f32=False, threads=1, **kw):
+    def make(cls, env_id, num_envs, seed=None, f32=False, threads=1, env_seed=None, **kw):
+        """Same seeding rule as the CUDA VecEnv: `seed` keys the per-env streams and, for Flagrun, an explicit one is
+        also the reference's ctor kwarg that seeds the shared goal stream (ant_flagrun_env.py:16,39)."""
+        from hrl_pybullet_envs_b200.config import HRL_ANT_FLAGRUN
         cfg = default_config(ENV_IDS[env_id], num_envs, **kw)
-        cfg.seed = seed
+        cfg.seed = int(seed or 0)
+        if ENV_IDS[env_id] == HRL_ANT_FLAGRUN and seed is not None:
+            cfg.flag_seed = int(seed)
+        if env_seed is not None:
+            cfg.seed = int(env_seed)
         return cls(cfg, f32=f32, threads=threads)
 
     def close(self):
