@@ -34,7 +34,10 @@ ENVS = {
     "AntMazeMj": ("AntMazeMjEnv-v0", 4096),
     "PointGather": ("PointGatherBulletEnv-v0", 4096),
 }
-SETTLE_STEPS = 40     # untimed steps before any timed region (both arms): the reset drops the ants 0.3 m (~15 steps airborne)
+# untimed steps before any timed region (both arms).  The reset drops the ants 0.3 m (~15 steps airborne: no contact rows);
+# the joint-limit rows take longer to reach their steady share under random actions (0.7 rows / sub-step after 40 steps,
+# 2.6 after 200, measured), so both arms settle for 200 steps.
+SETTLE_STEPS = 200
 GATE_CHUNK = 32       # timed steps enqueued behind one gate (4 stream operations each: well inside the launch queue)
 E2E_SEGMENTS = 5
 

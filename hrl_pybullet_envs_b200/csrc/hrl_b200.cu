@@ -10,12 +10,14 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
 
 #include "../../include/hrl_b200.h"
 #include "hrl_ant.cuh"
+#include "hrl_ant_wide.cuh"
 #include "hrl_math.cuh"
 #include "hrl_sensors.cuh"
 
@@ -53,6 +55,7 @@ struct hrl_handle {
   float *s_act, *s_obs, *s_rew, *s_info;
   uint8_t* s_done;
   size_t s_out_bytes;
+  int sub;        // lane mapping of the ant kernels: 1 = 4 lanes per env, 2 = 8, 4 = 16 (hrl_set_lanes_per_env)
   int host_mode;  // HRL_HOST_AUTO / HRL_HOST_COPY / HRL_HOST_ZEROCOPY
   unsigned int* h_flag;  // pinned host word polled by hrl_step_host (zero-copy mode)
   unsigned int seq;
@@ -184,29 +187,51 @@ __device__ __forceinline__ bool flag_next(const hrl_config& cfg, uint32_t genv, 
 //   mode 2: reset the masked envs and emit their observation, mode 3: observe only.
 // ------------------------------------------------------------------------------------------
 #define SMEM_PER_WARP_FLOATS (HRL_SMEM_FLOATS_PER_WARP + HRL_ITEM_SCRATCH_FLOATS)
-static_assert(HRL_ROWS_FLOATS_PER_WARP >= HRL_EPW * HRL_OBS_STAGE + 2 * HRL_EPW * 2 * HRL_MAX_BINS, "task-layer tiles must fit in the row buffer");
+static_assert(HRL_EPW == 8, "the 4-lane mapping fills a warp with 8 envs");
 
-template <int FAMILY>
-__global__ void __launch_bounds__(32 * HRL_WARPS_PER_CTA)
+// Lane mapping of the fused kernel.  SUB = lanes per leg: 1 = 4 lanes per env, 8 envs per warp (hrl_ant.cuh);
+// 2 / 4 = the wide mappings of hrl_ant_wide.cuh (8 / 16 lanes per env, 4 / 2 envs per warp).
+template <int SUB>
+struct Map : WideMap<SUB> {
+  static constexpr int ROW_F4 = HRLW_ROW_F4, ENV_F4 = HRLW_ENV_F4;
+  static constexpr int MIN_CTAS = (SUB == 4 ? 14 : 7) / HRL_WARPS_PER_CTA;  // all 4096 envs resident in one wave
+};
+template <>
+struct Map<1> {
+  static constexpr int LPE = 4, EPW = 8, IPL = 4, ROW_F4 = 4, ENV_F4 = HRL_ENV_F4;
+  static constexpr int ROWS_FLOATS = HRL_ROWS_FLOATS_PER_WARP, LAM_FLOATS = HRL_LAM_FLOATS_PER_WARP;
+  static constexpr int CAND_FLOATS = HRL_MAXC * HRL_CAND_F * 32, ITEM_FLOATS = HRL_ITEM_SCRATCH_FLOATS;
+  static constexpr int SMEM_FLOATS = SMEM_PER_WARP_FLOATS;
+  static constexpr int MIN_CTAS = 1;
+};
+template <int SUB>
+constexpr bool tiles_fit() { return Map<SUB>::ROWS_FLOATS >= Map<SUB>::EPW * HRL_OBS_STAGE + 2 * Map<SUB>::EPW * 2 * HRL_MAX_BINS; }
+static_assert(tiles_fit<1>() && tiles_fit<2>() && tiles_fit<4>(), "task-layer tiles must fit in the row buffer");
+
+template <int FAMILY, int SUB>
+__global__ void __launch_bounds__(32 * HRL_WARPS_PER_CTA, Map<SUB>::MIN_CTAS)
 ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float* __restrict__ bounds, int n_lines,
                const float* __restrict__ actions, const uint8_t* __restrict__ mask, float* __restrict__ obs_out,
                float* __restrict__ rew_out, uint8_t* __restrict__ done_out, float* __restrict__ info_out,
                float* __restrict__ term_out, int mode, int n_sub, int D) {
   extern __shared__ __align__(16) float smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, k = lane & 3, ew = lane >> 2, es = ew % HRL_EPW;
-  float* rows = smem + warp * SMEM_PER_WARP_FLOATS;
-  float* cands = rows + HRL_ROWS_FLOATS_PER_WARP + HRL_LAM_FLOATS_PER_WARP;
+  typedef Map<SUB> M;
+  constexpr int LPE = M::LPE, EPW = M::EPW, IPL = M::IPL;
+  // l: lane within the env, k: leg, sub: sub-lane of the leg (wide mappings), ew = es: env slot in the warp
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l = lane & (LPE - 1), k = l & 3, sub = l >> 2, ew = lane / LPE, es = ew;
+  float* rows = smem + warp * M::SMEM_FLOATS;
+  float* cands = rows + M::ROWS_FLOATS + M::LAM_FLOATS;
   // the task layer runs after the last sub-step, when the solver rows are dead: its observation staging tile and
   // the sensor bins alias the row buffer (keeps a warp at < 37.8 KB so that 6 CTAs fit an SM at large batch sizes)
   float* sobs = rows;                                                                   // [EPW][HRL_OBS_STAGE]
-  unsigned long long* sbins = (unsigned long long*)(rows + HRL_EPW * HRL_OBS_STAGE);   // [EPW][2][HRL_MAX_BINS]
-  float* iscr = cands + HRL_MAXC * HRL_CAND_F * 32;  // cube-collider scratch: lives across the sub-steps
+  unsigned long long* sbins = (unsigned long long*)(rows + EPW * HRL_OBS_STAGE);   // [EPW][2][HRL_MAX_BINS]
+  float* iscr = cands + M::CAND_FLOATS;  // cube-collider scratch: lives across the sub-steps
   const int N = cfg.num_envs, kind = cfg.env_kind;
-  const int env0 = (blockIdx.x * HRL_WARPS_PER_CTA + warp) * HRL_EPW;  // first env of this warp
+  const int env0 = (blockIdx.x * HRL_WARPS_PER_CTA + warp) * EPW;  // first env of this warp
   const int env_raw = env0 + ew;
-  const bool active = (ew < HRL_EPW) && (env_raw < N);
-  // idle lane groups shadow an env of their own warp (same trip counts, stores suppressed)
-  const int e = active ? env_raw : min(env0 + (ew % HRL_EPW), N - 1);
+  const bool active = env_raw < N;
+  // the lane groups of a ragged tail shadow the last env (same trip counts, stores suppressed)
+  const int e = active ? env_raw : N - 1;
   const uint32_t genv = (uint32_t)(cfg.env_index_offset + e);
   const LegConst lc = leg_const(k);
 
@@ -227,23 +252,33 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
     T.feet[0] = m1.x; T.feet[1] = m1.y; T.feet[2] = m1.z; T.feet[3] = m1.w;
     T.t = i0.x; T.episode = i0.y; T.steps_total = i0.z; T.goals_left = i0.w; T.since = i1.x; T.rewarded = i1.y; T.gen = i1.z;
   }
-  float it_x[4], it_y[4];
+  float it_x[IPL], it_y[IPL];  // this lane's items IPL * l .. IPL * l + IPL - 1 (food 0-7, poison 8-15)
   if (FAMILY == 0) {
-    const float4 a = st.items[(e * 4 + k) * 2 + 0], b = st.items[(e * 4 + k) * 2 + 1];
-    it_x[0] = a.x; it_y[0] = a.y; it_x[1] = a.z; it_y[1] = a.w; it_x[2] = b.x; it_y[2] = b.y; it_x[3] = b.z; it_y[3] = b.w;
+    if (IPL == 4) {
+      const float4 a = st.items[(e * 4 + l) * 2 + 0], b = st.items[(e * 4 + l) * 2 + 1];
+      it_x[0] = a.x; it_y[0] = a.y; it_x[1] = a.z; it_y[1] = a.w; it_x[IPL - 2] = b.x; it_y[IPL - 2] = b.y; it_x[IPL - 1] = b.z; it_y[IPL - 1] = b.w;
+    } else if (IPL == 2) {
+      const float4 a = st.items[e * 8 + l];
+      it_x[0] = a.x; it_y[0] = a.y; it_x[IPL - 1] = a.z; it_y[IPL - 1] = a.w;
+    } else {
+      const float2 a = reinterpret_cast<const float2*>(st.items)[e * 16 + l];
+      it_x[0] = a.x; it_y[0] = a.y;
+    }
   }
 
   // ---- physics ----
   float act1 = 0.f, act2 = 0.f;
   int feet_ground = 0;
-  int touch[4] = {0, 0, 0, 0};
+  int touch[IPL];
+#pragma unroll
+  for (int i = 0; i < IPL; i++) touch[i] = 0;
   if (mode <= 1) {
     // idle solver visits read the two all-zero rows HRL_ROW_ZERO, HRL_ROW_ZERO+1 and the idle impulse / mu slots
     // behind the real ones: zero those (2 x 4 float4 per env) and the whole impulse array, nothing else
-    for (int i = lane; i < 8 * HRL_EPW; i += 32)
-      reinterpret_cast<float4*>(rows)[(i >> 3) * HRL_ENV_F4 + HRL_ROW_ZERO * 4 + (i & 7)] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = lane; i < HRL_LAM_FLOATS_PER_WARP / 4; i += 32)
-      reinterpret_cast<float4*>(rows + HRL_ROWS_FLOATS_PER_WARP)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = lane; i < 2 * M::ROW_F4 * EPW; i += 32)
+      reinterpret_cast<float4*>(rows)[(i / (2 * M::ROW_F4)) * M::ENV_F4 + HRL_ROW_ZERO * M::ROW_F4 + (i % (2 * M::ROW_F4))] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = lane; i < M::LAM_FLOATS / 4; i += 32)
+      reinterpret_cast<float4*>(rows + M::ROWS_FLOATS)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
     const float2 a = reinterpret_cast<const float2*>(actions)[e * 4 + k];
     act1 = a.x; act2 = a.y;
@@ -257,18 +292,22 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       const bool on = (i == 0) || !cfg.torque_first_substep_only;
       // cube colliders (FAMILY 0): the contact points of the LAST sub-step are what getContactPoints reports
       // (ant_gather_env.py:114)
-      ant_substep<FAMILY == 0>(s, P, lc, on ? tau1 : 0.f, on ? tau2 : 0.f, rows, cands, lane, k, es, feet_ground, sc, sl, it_x, it_y,
-                               iscr, mode == 0 && i == ns - 1);
+      if (SUB == 1)
+        ant_substep<FAMILY == 0>(s, P, lc, on ? tau1 : 0.f, on ? tau2 : 0.f, rows, cands, lane, k, es, feet_ground, sc, sl, it_x, it_y,
+                                 iscr, mode == 0 && i == ns - 1);
+      else
+        ant_substep_w<(SUB > 1 ? SUB : 2), FAMILY == 0>(s, P, lc, on ? tau1 : 0.f, on ? tau2 : 0.f, rows, cands, lane, l, k, sub, es, feet_ground,
+                                                        sc, sl, it_x, it_y, iscr, mode == 0 && i == ns - 1);
     }
     if (FAMILY == 0 && P.item_contacts && mode == 0) {  // this lane's 4 cubes: contact points of the last sub-step
       __syncwarp();
-      const unsigned long long tw = reinterpret_cast<const unsigned long long*>(iscr + HRL_EPW * 32)[es];
+      const unsigned long long tw = reinterpret_cast<const unsigned long long*>(iscr + EPW * 32)[es];
 #pragma unroll
-      for (int i = 0; i < 4; i++) touch[i] = (int)((tw >> (4 * (4 * k + i))) & 15ull);
+      for (int i = 0; i < IPL; i++) touch[i] = (int)((tw >> (4 * (IPL * l + i))) & 15ull);
       __syncwarp();
     }
     if (st.stats) {  // warp-uniform: inactive tail lanes contribute zeros (never guard a *_sync by `active`)
-      const int na = __popc(__ballot_sync(HRL_FULL_MASK, active && k == 0));
+      const int na = __popc(__ballot_sync(HRL_FULL_MASK, active && l == 0));
       sc = __reduce_add_sync(HRL_FULL_MASK, active ? sc : 0); sl = __reduce_add_sync(HRL_FULL_MASK, active ? sl : 0);
       if (lane == 0) {
         atomicAdd(&st.stats[0], (unsigned long long)sc); atomicAdd(&st.stats[1], (unsigned long long)sl);
@@ -318,8 +357,8 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       if (FAMILY == 0) {
         // gather_scene.py:38-50: every item re-randomised, avoiding (0,0)
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int gi = 4 * k + i;
+        for (int i = 0; i < IPL; i++) {
+          const int gi = IPL * l + i;
           if (gi < cfg.n_food + cfg.n_poison) place_item(cfg, genv, STREAM_ITEM_RESET, (uint32_t)T.episode, gi, 0.f, 0.f, it_x[i], it_y[i]);
         }
         T.tx = 0.f; T.ty = 0.f;
@@ -336,8 +375,10 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
         if (kind == HRL_ANT_FLAGRUN) {
           if (T.episode == 0) { T.tx = 1000.f; T.ty = 0.f; }  // WalkerBase default walk target
           T.rewarded = 0;
-          if (cfg.flag_manual_goals) { T.goals_left = 0; set_pot = true; todo = 1; }  // ant_flagrun_env.py:150-153: no goals drawn, target kept
-          else { T.goals_left = cfg.flag_max_targets; todo = 2; }
+          // goal generation of the episode: reset() itself draws generation 0; in manual mode nothing is drawn yet, so
+          // the caller's first create_targets() (generation += 1) draws what the automatic mode would have drawn
+          if (cfg.flag_manual_goals) { T.goals_left = 0; T.gen = -1; set_pot = true; todo = 1; }  // ant_flagrun_env.py:150-153: no goals drawn, target kept
+          else { T.goals_left = cfg.flag_max_targets; T.gen = 0; todo = 2; }
         } else { set_pot = true; todo = 1; }
       }
       T.episode++;
@@ -382,8 +423,8 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       if (first && todo == 1) {
         // pickups in item order; each lane owns 4 items (:86-92, gather_scene.py:95-114)
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int gi = 4 * k + i;
+        for (int i = 0; i < IPL; i++) {
+          const int gi = IPL * l + i;
           if (gi >= cfg.n_food + cfg.n_poison) continue;
           const double dx = __dsub_rn((double)it_x[i], (double)s.O.x), dy = __dsub_rn((double)it_y[i], (double)s.O.y);
           const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
@@ -397,25 +438,25 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       const bool touch_pickup = first && todo == 1 && !(cfg.robot_coll_dist > 0.f);
       if (touch_pickup) {  // ant_gather_env.py:113-116: one reward_collision per contact POINT of the robot with a cube
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-          if (4 * k + i < cfg.n_food + cfg.n_poison) food_rew += (float)touch[i] * ((4 * k + i < cfg.n_food) ? 1.f : -1.f);
+        for (int i = 0; i < IPL; i++)
+          if (IPL * l + i < cfg.n_food + cfg.n_poison) food_rew += (float)touch[i] * ((IPL * l + i < cfg.n_food) ? 1.f : -1.f);
       }
-      food_rew = gsum(food_rew);
+      food_rew = esum<LPE>(food_rew);
       const int nb = cfg.n_bins;
       if (commit) {
-        if (k == 0) {
+        if (l == 0) {
           so[0] = o_z; so[1] = o_v0; so[2] = o_v1; so[3] = o_v2; so[4] = o_r; so[5] = o_p;
           so[22] = T.feet[0]; so[23] = T.feet[1]; so[24] = T.feet[2]; so[25] = T.feet[3];
         }
-        so[6 + 4 * k] = clip5(rel1); so[7 + 4 * k] = clip5(sp1); so[8 + 4 * k] = clip5(rel2); so[9 + 4 * k] = clip5(sp2);
+        if (sub == 0) { so[6 + 4 * k] = clip5(rel1); so[7 + 4 * k] = clip5(sp1); so[8 + 4 * k] = clip5(rel2); so[9 + 4 * k] = clip5(sp2); }
       }
       if (cfg.use_sensor) {
         // sector sensor (:128-177): nearest item wins per bin
-        for (int i = lane; i < HRL_EPW * 2 * HRL_MAX_BINS; i += 32) sbins[i] = 0x7ff0000000000000ull;
+        for (int i = lane; i < EPW * 2 * HRL_MAX_BINS; i += 32) sbins[i] = 0x7ff0000000000000ull;
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int gi = 4 * k + i;
+        for (int i = 0; i < IPL; i++) {
+          const int gi = IPL * l + i;
           if (gi >= cfg.n_food + cfg.n_poison) continue;
           double d2;
           const int b = gather_item_bin(s.O.x, s.O.y, yaw, it_x[i], it_y[i], nb, cfg.sensor_range, cfg.sensor_span, &d2);
@@ -423,7 +464,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
         }
         __syncwarp();
         if (commit) {
-          for (int b = k; b < 2 * nb; b += 4) {
+          for (int b = l; b < 2 * nb; b += LPE) {
             const int ty = b / nb, bb = b - ty * nb;
             const unsigned long long bits = sbins[(es * 2 + ty) * HRL_MAX_BINS + bb];
             so[26 + b] = bits == 0x7ff0000000000000ull ? 0.f : (float)(1.0 - __longlong_as_double((long long)bits) / (double)cfg.sensor_range);
@@ -434,19 +475,19 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
         // poison items, each sorted by squared distance (stable).  Rank = number of same-type items that sort
         // before this one; the 16 exact float64 distances are exchanged through shared memory.
         double* sd2 = reinterpret_cast<double*>(sbins + es * 2 * HRL_MAX_BINS);
-        double d2v[4];
+        double d2v[IPL];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < IPL; i++) {
           const double dx = __dsub_rn((double)it_x[i], (double)s.O.x), dy = __dsub_rn((double)it_y[i], (double)s.O.y);
           d2v[i] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-          sd2[4 * k + i] = d2v[i];
+          sd2[IPL * l + i] = d2v[i];
         }
         __syncwarp();
         if (commit) {
           const int keep_f = min(nb, cfg.n_food), keep_p = min(nb, cfg.n_poison);
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const int gi = 4 * k + i;
+          for (int i = 0; i < IPL; i++) {
+            const int gi = IPL * l + i;
             if (gi >= cfg.n_food + cfg.n_poison) continue;
             const bool poison = gi >= cfg.n_food;
             const int first = poison ? cfg.n_food : 0, cnt = poison ? cfg.n_poison : cfg.n_food;
@@ -462,8 +503,8 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       }
       if (touch_pickup) {  // the cube moves AFTER the observation of this step was built (:96 before :113)
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int gi = 4 * k + i;
+        for (int i = 0; i < IPL; i++) {
+          const int gi = IPL * l + i;
           if (gi >= cfg.n_food + cfg.n_poison || touch[i] == 0) continue;
           if (cfg.respawn) place_item(cfg, genv, STREAM_ITEM, (uint32_t)T.steps_total, gi, s.O.x, s.O.y, it_x[i], it_y[i]);
           else { it_x[i] = 100.f; it_y[i] = 0.f; }
@@ -481,7 +522,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
         if (cfg.max_episode_steps > 0 && T.t >= cfg.max_episode_steps) { trunc = done ? 0.f : 1.f; done = 1; }
         T.ret += food_rew + dead_rew;
         if (done) { T.ret_sum += T.ret; T.ret = 0.f; }
-        if (active && k == 0) {
+        if (active && l == 0) {
           rew_out[e] = food_rew + dead_rew;
           done_out[e] = (uint8_t)done;
           if (info_out) reinterpret_cast<float4*>(info_out)[e] = make_float4(food_rew, dead_rew, trunc, (float)T.t);
@@ -493,47 +534,49 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       if (commit) {
         if (mj) {
           // MjAnt.calc_state envs/MjAnt.py:17-25: [pos3, quat4, q8, lin3, ang3, qd8] unclipped
-          if (k == 0) {
+          if (l == 0) {
             so[0] = s.O.x; so[1] = s.O.y; so[2] = s.O.z; so[3] = s.qx; so[4] = s.qy; so[5] = s.qz; so[6] = s.qw;
             so[15] = s.v.x; so[16] = s.v.y; so[17] = s.v.z; so[18] = s.w.x; so[19] = s.w.y; so[20] = s.w.z;
           }
-          so[7 + 2 * k] = s.q1; so[8 + 2 * k] = s.q2; so[21 + 2 * k] = s.qd1; so[22 + 2 * k] = s.qd2;
+          if (sub == 0) { so[7 + 2 * k] = s.q1; so[8 + 2 * k] = s.q2; so[21 + 2 * k] = s.qd1; so[22 + 2 * k] = s.qd2; }
           if (kind == HRL_ANT_MAZE_MJ) {  // ant_maze_mj_env.py:57-64
             const int nb = cfg.n_bins;
-            for (int b = k; b < nb; b += 4) {
+            for (int b = l; b < nb; b += LPE) {
               so[29 + b] = lidar_ray(b, nb, cfg.sensor_span, cfg.sensor_range, n_lines, bounds, s.O.x, s.O.y, yaw);
               so[29 + nb + b] = 0.f; so[29 + 2 * nb + b] = 0.f;
             }
-            if (k == 0) so[29 + 3 * nb] = (float)T.t * 0.001f;
+            if (l == 0) so[29 + 3 * nb] = (float)T.t * 0.001f;
           }
         } else {
           const int off = (kind == HRL_ANT_FLAGRUN) ? 2 : 0;  // Flagrun keeps sin/cos of the target angle
-          if (k == 0) {
+          if (l == 0) {
             so[0] = o_z;
             if (off) { so[1] = clip5(sin_t); so[2] = clip5(cos_t); }
             so[1 + off] = o_v0; so[2 + off] = o_v1; so[3 + off] = o_v2; so[4 + off] = o_r; so[5 + off] = o_p;
             so[22 + off] = T.feet[0]; so[23 + off] = T.feet[1]; so[24 + off] = T.feet[2]; so[25 + off] = T.feet[3];
           }
-          so[6 + off + 4 * k] = clip5(rel1); so[7 + off + 4 * k] = clip5(sp1);
-          so[8 + off + 4 * k] = clip5(rel2); so[9 + off + 4 * k] = clip5(sp2);
+          if (sub == 0) {
+            so[6 + off + 4 * k] = clip5(rel1); so[7 + off + 4 * k] = clip5(sp1);
+            so[8 + off + 4 * k] = clip5(rel2); so[9 + off + 4 * k] = clip5(sp2);
+          }
           if (kind == HRL_ANT_MAZE) {
             int nt = 2;
             if (cfg.sense_target) {  // ant_maze_bullet_env.py:135-178: wtd is the Q1-distorted distance, the pose the true one
               nt = cfg.n_bins;
               const int tb = maze_target_bin(cfg.n_bins, cfg.sensor_span, cfg.sensor_range, cfg.has_box ? 3 : 0, bounds + 16, s.O.x,
                                              s.O.y, yaw, T.tx, T.ty, wtd_new);
-              for (int b = k; b < nt; b += 4) so[26 + b] = (b == tb) ? (float)(1.0 - (double)wtd_new / (double)cfg.sensor_range) : 0.f;
-            } else if (k == 0) {  // ant_maze_bullet_env.py:123-133 (true torso xy, not the Q1 mean)
+              for (int b = l; b < nt; b += LPE) so[26 + b] = (b == tb) ? (float)(1.0 - (double)wtd_new / (double)cfg.sensor_range) : 0.f;
+            } else if (l == 0) {  // ant_maze_bullet_env.py:123-133 (true torso xy, not the Q1 mean)
               const float vx = T.tx - s.O.x, vy = T.ty - s.O.y;
               if (cfg.target_encoding == 0) { const float nn = sqrtf(vx * vx + vy * vy); so[26] = vx / nn; so[27] = vy / nn; }
               else { float sa, ca; sincosf(atan2f(vy, vx) - yaw, &sa, &ca); so[26] = sa; so[27] = ca; }
             }
             if (cfg.sense_walls)
-              for (int b = k; b < cfg.n_bins; b += 4)
+              for (int b = l; b < cfg.n_bins; b += LPE)
                 so[26 + nt + b] = lidar_ray(b, cfg.n_bins, cfg.sensor_span, cfg.sensor_range, n_lines, bounds, s.O.x, s.O.y, yaw);
           }
           if (kind == HRL_ANT_FLAGRUN && cfg.flag_use_sensor)  // ant_flagrun_env.py:122-130 (body_real_xyz = torso)
-            for (int b = k; b < cfg.n_bins; b += 4)
+            for (int b = l; b < cfg.n_bins; b += LPE)
               so[28 + b] = lidar_ray(b, cfg.n_bins, cfg.sensor_span, cfg.sensor_range, n_lines, bounds, s.O.x, s.O.y, yaw);
         }
       }
@@ -600,7 +643,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
         if (cfg.max_episode_steps > 0 && T.t >= cfg.max_episode_steps) { trunc = done ? 0.f : 1.f; done = 1; }
         T.ret += rew;
         if (done) { T.ret_sum += T.ret; T.ret = 0.f; }
-        if (active && k == 0) {
+        if (active && l == 0) {
           rew_out[e] = rew;
           done_out[e] = (uint8_t)done;
           // info[2]: bit 0 = TimeLimit.truncated, bit 1 = the walk target changed in this step (info['target'] is set)
@@ -621,9 +664,9 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
     const unsigned need_mask = __ballot_sync(HRL_FULL_MASK, next_todo == 3);
     if (need_mask && term_out) {
       __syncwarp();
-      for (int i = lane; i < HRL_EPW * D; i += 32) {
+      for (int i = lane; i < EPW * D; i += 32) {
         const int w8 = i / D;
-        if (((need_mask >> (4 * w8)) & 1u) && env0 + w8 < N) term_out[(size_t)env0 * D + i] = sobs[i];
+        if (((need_mask >> (LPE * w8)) & 1u) && env0 + w8 < N) term_out[(size_t)env0 * D + i] = sobs[i];
       }
       __syncwarp();
     }
@@ -633,7 +676,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
 
   // ---- store ----
   if (active) {
-    if (k == 0) {
+    if (l == 0) {
       st.base[e * 4 + 0] = make_float4(s.O.x, s.O.y, s.O.z, T.initial_z);
       st.base[e * 4 + 1] = make_float4(s.qx, s.qy, s.qz, s.qw);
       st.base[e * 4 + 2] = make_float4(s.v.x, s.v.y, s.v.z, T.potential);
@@ -643,10 +686,16 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       st.misci[e * 2 + 0] = make_int4(T.t, T.episode, T.steps_total, T.goals_left);
       st.misci[e * 2 + 1] = make_int4(T.since, T.rewarded, T.gen, 0);
     }
-    st.leg[e * 4 + k] = make_float4(s.q1, s.q2, s.qd1, s.qd2);
+    if (sub == 0) st.leg[e * 4 + k] = make_float4(s.q1, s.q2, s.qd1, s.qd2);
     if (FAMILY == 0) {
-      st.items[(e * 4 + k) * 2 + 0] = make_float4(it_x[0], it_y[0], it_x[1], it_y[1]);
-      st.items[(e * 4 + k) * 2 + 1] = make_float4(it_x[2], it_y[2], it_x[3], it_y[3]);
+      if (IPL == 4) {
+        st.items[(e * 4 + l) * 2 + 0] = make_float4(it_x[0], it_y[0], it_x[1], it_y[1]);
+        st.items[(e * 4 + l) * 2 + 1] = make_float4(it_x[IPL - 2], it_y[IPL - 2], it_x[IPL - 1], it_y[IPL - 1]);
+      } else if (IPL == 2) {
+        st.items[e * 8 + l] = make_float4(it_x[0], it_y[0], it_x[IPL - 1], it_y[IPL - 1]);
+      } else {
+        reinterpret_cast<float2*>(st.items)[e * 16 + l] = make_float2(it_x[0], it_y[0]);
+      }
     }
   }
   if (mode != 1 && obs_out) {
@@ -658,13 +707,13 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       wmask = __ballot_sync(HRL_FULL_MASK, m);
     }
     float* dst = obs_out + (size_t)env0 * D;
-    if (env0 + HRL_EPW <= N && wmask == 0xffffffffu && ((HRL_EPW * D) & 3) == 0 && (((uintptr_t)dst & 15) == 0)) {
+    if (env0 + EPW <= N && wmask == 0xffffffffu && ((EPW * D) & 3) == 0 && (((uintptr_t)dst & 15) == 0)) {
       // common case: one contiguous, 16-byte aligned span -> float4 stores, no index arithmetic
-      for (int i = lane; i < HRL_EPW * D / 4; i += 32) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(sobs)[i];
+      for (int i = lane; i < EPW * D / 4; i += 32) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(sobs)[i];
     } else {
-      for (int i = lane; i < HRL_EPW * D; i += 32) {
+      for (int i = lane; i < EPW * D; i += 32) {
         const int w8 = i / D;
-        if (env0 + w8 < N && ((wmask >> (4 * w8)) & 1u)) dst[i] = sobs[i];
+        if (env0 + w8 < N && ((wmask >> (LPE * w8)) & 1u)) dst[i] = sobs[i];
       }
     }
   }
@@ -1106,6 +1155,23 @@ static int validate(const hrl_config* c) {
   return HRL_OK;
 }
 
+// Lane mapping used by new handles: HRL_B200_LANES = 4 | 8 | 16 lanes per env (A/B runs); default HRL_DEFAULT_LANES.
+#ifndef HRL_DEFAULT_LANES
+#define HRL_DEFAULT_LANES 4
+#endif
+static int default_sub() {
+  int lanes = HRL_DEFAULT_LANES;
+  if (const char* e = getenv("HRL_B200_LANES")) lanes = atoi(e);
+  return lanes == 16 ? 4 : (lanes == 8 ? 2 : 1);
+}
+
+int hrl_set_lanes_per_env(hrl_handle* h, int32_t lanes) {
+  if (!h || (lanes != 4 && lanes != 8 && lanes != 16)) return set_err(HRL_E_INVALID, "lanes per env must be 4, 8 or 16");
+  h->sub = lanes / 4;
+  return HRL_OK;
+}
+int hrl_get_lanes_per_env(const hrl_handle* h) { return h ? 4 * h->sub : -1; }
+
 int hrl_destroy(hrl_handle* h) {
   if (!h) return HRL_OK;
   DeviceGuard guard(h->device);
@@ -1167,13 +1233,15 @@ int hrl_create(const hrl_config* cfg, int32_t device, hrl_handle** out) {
   float b[28];
   h->n_lines = scene_bounds(cfg, b);
   CKH(cudaMemcpy(h->d_bounds, b, sizeof b, cudaMemcpyHostToDevice));
-  // opt in to the dynamic shared memory the ant kernels need
-  const int smem = HRL_WARPS_PER_CTA * SMEM_PER_WARP_FLOATS * (int)sizeof(float);
-  CKH(cudaFuncSetAttribute(ant_env_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CKH(cudaFuncSetAttribute(ant_env_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  // the kernels live in shared memory and registers (hardly any L1 traffic): take the whole carve-out, 6 CTAs / SM
-  CKH(cudaFuncSetAttribute(ant_env_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CKH(cudaFuncSetAttribute(ant_env_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  // opt in to the dynamic shared memory the ant kernels need; they live in shared memory and registers (hardly any
+  // L1 traffic): take the whole carve-out
+#define OPT_IN(FAM, SUB)                                                                                                      \
+  CKH(cudaFuncSetAttribute(ant_env_kernel<FAM, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,                             \
+                           HRL_WARPS_PER_CTA * Map<SUB>::SMEM_FLOATS * (int)sizeof(float)));                                  \
+  CKH(cudaFuncSetAttribute(ant_env_kernel<FAM, SUB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
+  OPT_IN(0, 1); OPT_IN(1, 1); OPT_IN(0, 2); OPT_IN(1, 2); OPT_IN(0, 4); OPT_IN(1, 4);
+#undef OPT_IN
+  h->sub = default_sub();
   // like the reference, reset() must be called before the first step(); an un-reset env has a
   // zero quaternion, produces a non-finite observation and is ended by the NaN guard
   CKH(cudaDeviceSynchronize());
@@ -1196,12 +1264,19 @@ static int launch_env(hrl_handle* h, int mode, int n_sub, const float* act, cons
     const int B = 16 * HRL_POINT_EPB, G = (h->N + HRL_POINT_EPB - 1) / HRL_POINT_EPB;
     point_env_kernel<<<G, B, 0, s>>>(h->cfg, h->st, act, mask, obs, rew, done, info, term, mode, n_sub, h->D);
   } else {
-    const int T = 32 * HRL_WARPS_PER_CTA, EPC = HRL_EPW * HRL_WARPS_PER_CTA, G = (h->N + EPC - 1) / EPC;
-    const size_t smem = (size_t)HRL_WARPS_PER_CTA * SMEM_PER_WARP_FLOATS * sizeof(float);
-    if (h->cfg.env_kind == HRL_ANT_GATHER)
-      ant_env_kernel<0><<<G, T, smem, s>>>(h->cfg, st, h->d_bounds, h->n_lines, act, mask, obs, rew, done, info, term, mode, n_sub, h->D);
-    else
-      ant_env_kernel<1><<<G, T, smem, s>>>(h->cfg, st, h->d_bounds, h->n_lines, act, mask, obs, rew, done, info, term, mode, n_sub, h->D);
+    const int T = 32 * HRL_WARPS_PER_CTA;
+#define LAUNCH(FAM, SUB)                                                                                                     \
+  do {                                                                                                                       \
+    const int EPC = Map<SUB>::EPW * HRL_WARPS_PER_CTA, G = (h->N + EPC - 1) / EPC;                                           \
+    const size_t smem = (size_t)HRL_WARPS_PER_CTA * Map<SUB>::SMEM_FLOATS * sizeof(float);                                   \
+    ant_env_kernel<FAM, SUB><<<G, T, smem, s>>>(h->cfg, st, h->d_bounds, h->n_lines, act, mask, obs, rew, done, info, term,  \
+                                                mode, n_sub, h->D);                                                          \
+  } while (0)
+    const bool gather = h->cfg.env_kind == HRL_ANT_GATHER;
+    if (h->sub == 4) { if (gather) LAUNCH(0, 4); else LAUNCH(1, 4); }
+    else if (h->sub == 2) { if (gather) LAUNCH(0, 2); else LAUNCH(1, 2); }
+    else { if (gather) LAUNCH(0, 1); else LAUNCH(1, 1); }
+#undef LAUNCH
   }
   g_launches++;
   CK(cudaGetLastError());

@@ -226,6 +226,12 @@ int hrl_sense_walls(int32_t M, int32_t n_bins, float span, float range, int32_t 
  * replaces scene.global_step() -> p.stepSimulation() (ant_gather_env.py:78). */
 int hrl_substeps(hrl_handle* h, const float* d_actions, int32_t n_sub, void* stream);
 
+/* Lane mapping of the fused Ant kernels (a tuning knob, not part of the reference's surface): 4 lanes per env
+ * (8 envs per warp), 8 (4 envs per warp) or 16 (2 envs per warp); results are identical up to float rounding.
+ * New handles take the library default, or HRL_B200_LANES from the environment.  DESIGN.md section 4. */
+int hrl_set_lanes_per_env(hrl_handle* h, int32_t lanes);
+int hrl_get_lanes_per_env(const hrl_handle* h);
+
 /* In-kernel counters feeding the FLOP model of bench.py (SURVEY.md section 5 "in-kernel optional counters"):
  * out = {contacts, joint-limit rows, env-substeps, reserved} accumulated since the last reset; synchronises. */
 int hrl_get_stats(hrl_handle* h, unsigned long long out[4], int reset);

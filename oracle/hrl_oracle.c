@@ -1345,10 +1345,10 @@ static void reset_env(hrlo_env* E, int e, real* obs) {
     s->wtd = c.wtd;
     s->rewarded = 0;
     if (cfg->flag_manual_goals) { /* :150-153: goals.clear(), nothing drawn, the walk target stays; potential as in WalkerBase.reset */
-      s->goals_left = 0;
+      s->goals_left = 0; s->goal_gen = -1; /* the caller's first create_targets() draws generation 0, like the automatic mode */
       s->potential = -s->wtd / (real)cfg->dt;
     } else {
-      s->goals_left = cfg->flag_max_targets;
+      s->goals_left = cfg->flag_max_targets; s->goal_gen = 0;
       flag_next_target(E, e, s, s->episode, &c, 1);
     }
   } else if (is_ant(kind)) {
