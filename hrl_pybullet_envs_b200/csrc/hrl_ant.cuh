@@ -402,7 +402,7 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
                                             float tau2, float* __restrict__ rows, float* __restrict__ cands,
                                             int lane, int k, int es, int& feet_ground, int& stat_contacts, int& stat_limits,
                                             const float* it_x = nullptr, const float* it_y = nullptr, float* iscr = nullptr,
-                                            bool count_touch = false) {
+                                            bool count_touch = false, int* trips = nullptr, float* dbg = nullptr) {
   const LegKin K = leg_fk(s, lc);
   const V3 a1 = K.ez, a2 = K.a2;
   const V3 r_ac = K.rh + K.r1;           // aux COM - O
@@ -484,6 +484,11 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
     }
   }
 
+  if (dbg) {  // debugging builds (HRL_DEBUG_CONTACTS): this leg's candidate list
+    dbg[0] = (float)nC;
+    for (int c = 0; c < nC; c++)
+      for (int f = 0; f < HRL_CAND_F; f++) dbg[1 + c * HRL_CAND_F + f] = CAND(c, f);
+  }
   // ---------------- smooth dynamics: bias forces, leg elimination, base Schur complement ----------
   LegDyn D;
   float ub[6], u1, u2;  // generalized velocity after the unconstrained update
@@ -699,6 +704,7 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
 #pragma unroll
   for (int i = 0; i < 7; i++) dv[i] = make_float2(0.f, 0.f);
   const int maxNL = __reduce_max_sync(HRL_FULL_MASK, NL), maxNC = __reduce_max_sync(HRL_FULL_MASK, NC);
+  if (trips) *trips += maxNL + (maxNC << 16);  // profiling builds (HRL_WARP_TIMES): the warp's solver trip counts
 #define HRL_LIM_ROW(t) (((t) < NL) ? lbase + lstep * (t) : HRL_ROW_ZERO)
 #define HRL_LIM_LAM(t, r) (lamL + (((t) < NL) ? (r) : 8))
 #define HRL_SLOT(t) (((t) < NC) ? (t) : HRL_NSLOT)

@@ -406,7 +406,7 @@ template <int SUB, bool ITEMS>
 __device__ __forceinline__ void ant_substep_w(AntLane& s, const SubstepParams& P, const LegConst& lc, float tau1, float tau2,
                                               float* __restrict__ rows, float* __restrict__ cands, int lane, int l, int k, int sub, int es,
                                               int& feet_ground, int& stat_contacts, int& stat_limits, const float* it_x = nullptr,
-                                              const float* it_y = nullptr, float* iscr = nullptr, bool count_touch = false) {
+                                              const float* it_y = nullptr, float* iscr = nullptr, bool count_touch = false, float* dbg = nullptr) {
   typedef WideMap<SUB> M;
   constexpr int LPE = M::LPE, GS = 4 * M::EPW;
   const int ebase = lane & ~(LPE - 1), gl = es * 4 + k;
@@ -452,25 +452,31 @@ __device__ __forceinline__ void ant_substep_w(AntLane& s, const SubstepParams& P
 #pragma unroll
     for (int o = 4; o < LPE; o <<= 1) feet |= __shfl_xor_sync(HRL_FULL_MASK, feet, o);
     feet_ground = feet;
-    if (n_mine > 0) {
+    // warp-uniform on purpose.  Guarded per lane (`if (n_mine > 0)`) this pass miscomputed on the B200 whenever only some
+    // lanes took the branch around the out-of-line cube tests (measured with tools/debug_wide.py: identical candidate
+    // lists, different solves); with every lane inside, the wide and the 4-lane mapping agree to rounding.
+    if (__any_sync(HRL_FULL_MASK, n_mine > 0)) {
       int dummy = 0;
       leg_spheres_w<GS, ITEMS>(s, P, K.rh, r_ank, r_tip, k, si0, si1, incl - n_mine, cands, gl, imask, ixy, itouch, count_touch, dummy);
     }
     if (!ITEMS && P.has_box) {  // capsule cylinders vs the box's vertical edges: after the spheres, by sub-lane 0 of the leg
       const float reach = 1.1314f + ant::R_CAPS + P.margin;
       const float nx = fmaxf(fmaxf(P.blo[0] - s.O.x, s.O.x - P.bhi[0]), 0.f), ny = fmaxf(fmaxf(P.blo[1] - s.O.y, s.O.y - P.bhi[1]), 0.f);
-      if (nx * nx + ny * ny < reach * reach) {
-        int ne = 0;
-        if (sub == 0)
-          ne = capsules_vs_box_edges_w<GS>(s.O, K.rh, r_ank, r_tip, P.blo[0], P.blo[1], P.blo[2], P.bhi[0], P.bhi[1], P.bhi[2], P.margin, cands, gl,
-                                           total, 0);
-        total += __shfl_sync(HRL_FULL_MASK, ne, ebase | k);
-      }
+      int ne = 0;
+      if (sub == 0 && nx * nx + ny * ny < reach * reach)
+        ne = capsules_vs_box_edges_w<GS>(s.O, K.rh, r_ank, r_tip, P.blo[0], P.blo[1], P.blo[2], P.bhi[0], P.bhi[1], P.bhi[2], P.margin, cands, gl,
+                                         total, 0);
+      total += __shfl_sync(HRL_FULL_MASK, ne, ebase | k);  // (outside the cull: every lane of the warp takes part in the shuffle)
     }
     nC = min(total, HRL_MAXC);
     __syncwarp();
   }
 
+  if (dbg && sub == 0) {  // debugging builds (HRL_DEBUG_CONTACTS): this leg's candidate list
+    dbg[0] = (float)nC;
+    for (int c = 0; c < nC; c++)
+      for (int f = 0; f < HRL_CAND_F; f++) dbg[1 + c * HRL_CAND_F + f] = CANDW(c, f);
+  }
   // ---------------- smooth dynamics (replicated in the sub-lanes of the leg) ----------------
   LegDyn D;
   float ub[6], u1, u2;

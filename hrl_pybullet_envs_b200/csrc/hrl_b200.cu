@@ -42,6 +42,10 @@ struct DevState {
   unsigned int* fin_count;
   unsigned int* fin_flag;
   unsigned int fin_seq;
+#ifdef HRL_WARP_TIMES
+  // profiling build only: per warp (cycles of the launch, cycles of the physics loop, solver trips, task-layer passes)
+  unsigned long long* wt;
+#endif
 };
 
 struct hrl_handle {
@@ -208,6 +212,10 @@ template <int SUB>
 constexpr bool tiles_fit() { return Map<SUB>::ROWS_FLOATS >= Map<SUB>::EPW * HRL_OBS_STAGE + 2 * Map<SUB>::EPW * 2 * HRL_MAX_BINS; }
 static_assert(tiles_fit<1>() && tiles_fit<2>() && tiles_fit<4>(), "task-layer tiles must fit in the row buffer");
 
+#ifdef HRL_DEBUG_CONTACTS
+__device__ float* g_dbg_contacts = nullptr;  // [N][4 legs][40]: candidate lists of the first sub-step of the last launch
+#endif
+
 template <int FAMILY, int SUB>
 __global__ void __launch_bounds__(32 * HRL_WARPS_PER_CTA, Map<SUB>::MIN_CTAS)
 ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float* __restrict__ bounds, int n_lines,
@@ -235,6 +243,11 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
   const uint32_t genv = (uint32_t)(cfg.env_index_offset + e);
   const LegConst lc = leg_const(k);
 
+#ifdef HRL_WARP_TIMES
+  const long long wt_t0 = clock64();
+  long long wt_t1 = wt_t0;
+  int wt_trips = 0, wt_passes = 0, wt_resets = 0;
+#endif
   // ---- load ----
   AntLane s;
   TaskRegs T;
@@ -294,10 +307,22 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       // (ant_gather_env.py:114)
       if (SUB == 1)
         ant_substep<FAMILY == 0>(s, P, lc, on ? tau1 : 0.f, on ? tau2 : 0.f, rows, cands, lane, k, es, feet_ground, sc, sl, it_x, it_y,
-                                 iscr, mode == 0 && i == ns - 1);
+                                 iscr, mode == 0 && i == ns - 1
+#if defined(HRL_WARP_TIMES) || defined(HRL_DEBUG_CONTACTS)
+#ifdef HRL_WARP_TIMES
+                                 , &wt_trips
+#else
+                                 , nullptr, (g_dbg_contacts && i == 0) ? g_dbg_contacts + (size_t)(e * 4 + k) * 40 : nullptr
+#endif
+#endif
+        );
       else
         ant_substep_w<(SUB > 1 ? SUB : 2), FAMILY == 0>(s, P, lc, on ? tau1 : 0.f, on ? tau2 : 0.f, rows, cands, lane, l, k, sub, es, feet_ground,
-                                                        sc, sl, it_x, it_y, iscr, mode == 0 && i == ns - 1);
+                                                        sc, sl, it_x, it_y, iscr, mode == 0 && i == ns - 1
+#ifdef HRL_DEBUG_CONTACTS
+                                                        , (g_dbg_contacts && i == 0) ? g_dbg_contacts + (size_t)(e * 4 + k) * 40 : nullptr
+#endif
+        );
     }
     if (FAMILY == 0 && P.item_contacts && mode == 0) {  // this lane's 4 cubes: contact points of the last sub-step
       __syncwarp();
@@ -316,6 +341,9 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
     }
   }
 
+#ifdef HRL_WARP_TIMES
+  wt_t1 = clock64();
+#endif
   // the lidar's bound lines (<= 7 x 4 floats): fetched once per warp and parked in shared memory (the contact
   // candidates are dead by now) - the ray loop would otherwise wait for a global load per line and ray
   if (FAMILY == 1) {
@@ -662,6 +690,9 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       } else if (done && cfg.auto_reset) next_todo = 3;
     } else if (todo == 1 && pend_reset) { next_todo = 3; pend_reset = false; }
     const unsigned need_mask = __ballot_sync(HRL_FULL_MASK, next_todo == 3);
+#ifdef HRL_WARP_TIMES
+    wt_passes++; wt_resets += __popc(need_mask) / LPE;
+#endif
     if (need_mask && term_out) {
       __syncwarp();
       for (int i = lane; i < EPW * D; i += 32) {
@@ -717,6 +748,13 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       }
     }
   }
+#ifdef HRL_WARP_TIMES
+  if (st.wt && lane == 0) {
+    unsigned long long* w = st.wt + 4 * (size_t)(blockIdx.x * HRL_WARPS_PER_CTA + warp);
+    w[0] = (unsigned long long)(clock64() - wt_t0); w[1] = (unsigned long long)(wt_t1 - wt_t0);
+    w[2] = (unsigned long long)wt_trips; w[3] = (unsigned long long)(wt_passes | (wt_resets << 8));
+  }
+#endif
   if (st.fin_flag) {
     // release at device scope by every writer; the last CTA acquires through the counter and then
     // publishes with a system-scope fence (fences are cumulative; PCIe posted writes stay ordered)
@@ -1142,7 +1180,9 @@ static int validate(const hrl_config* c) {
   if (hrl_obs_dim(c) > HRL_OBS_STAGE) return set_err(HRL_E_INVALID, "observation wider than 64");
   if (c->n_bins < 1 || c->n_bins > HRL_MAX_BINS) return set_err(HRL_E_INVALID, "n_bins out of range");
   if (c->n_food < 0 || c->n_food > 8 || c->n_poison < 0 || c->n_poison > 8) return set_err(HRL_E_INVALID, "n_food/n_poison out of range");
-  if (c->substeps < 1 || c->solver_iters < 0) return set_err(HRL_E_INVALID, "bad substeps/solver_iters");
+  // substeps == 0: a step runs the task layer on the current state only (how the parity tests feed the reference's
+  // step-level golden vectors through the kernels)
+  if (c->substeps < 0 || c->solver_iters < 0) return set_err(HRL_E_INVALID, "bad substeps/solver_iters");
   if (c->n_targets > HRL_MAX_TARGETS || c->flag_max_targets > 127) return set_err(HRL_E_INVALID, "too many targets");
   if (c->env_kind == HRL_POINT_GATHER && (c->item_contacts || !(c->robot_coll_dist > 0.f)))
     return set_err(HRL_E_INVALID, "PointGather cube colliders / contact-based pickup are not built");
@@ -1210,6 +1250,9 @@ int hrl_create(const hrl_config* cfg, int32_t device, hrl_handle** out) {
   ALLOC(h->st.misci, N * 2 * sizeof(int4));
   ALLOC(h->st.stats, 4 * sizeof(unsigned long long));
   ALLOC(h->st.fin_count, sizeof(unsigned int));
+#ifdef HRL_WARP_TIMES
+  ALLOC(h->st.wt, (N + 1) * 4 * sizeof(unsigned long long));
+#endif
   if (cudaHostAlloc((void**)&h->h_flag, 64, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); h->h_flag = nullptr; }
   else *h->h_flag = 0;
   ALLOC(h->d_bounds, 7 * 4 * sizeof(float));
@@ -1482,6 +1525,23 @@ int hrl_stream_gate(const uint32_t* d_flag, uint32_t expect, uint64_t timeout_ns
   CK(cudaGetLastError());
   return HRL_OK;
 }
+
+#ifdef HRL_DEBUG_CONTACTS
+int hrl_debug_contacts(float* d_buf) {  // debugging build: where the kernels dump the candidate lists (NULL: off)
+  CK(cudaMemcpyToSymbol(g_dbg_contacts, &d_buf, sizeof d_buf));
+  return HRL_OK;
+}
+#endif
+#ifdef HRL_WARP_TIMES
+/* profiling build (tools/warp_times.py): per-warp records of the LAST ant-kernel launch, 4 x u64 per warp */
+int hrl_debug_warp_times(hrl_handle* h, unsigned long long* out, int n_warps) {
+  if (!h || !out) return set_err(HRL_E_INVALID, "null argument");
+  ON_DEVICE(h->device);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, h->st.wt, (size_t)n_warps * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return HRL_OK;
+}
+#endif
 
 /* instrumentation for the FLOP model (bench.py roofline): contacts, limit rows, env-substeps */
 int hrl_get_stats(hrl_handle* h, unsigned long long out[4], int reset) {

@@ -1292,6 +1292,13 @@ static int maze_task(const hrl_config* cfg, const env_state* s, real inner, int 
   return done;
 }
 
+/* AntMazeMjEnv.step after the inner AntMjEnv step (ant_maze_mj_env.py:73-77). */
+static int maze_mj_task(const hrl_config* cfg, const env_state* s, real inner, int done, real* rew) {
+  *rew = inner * (real)cfg->inner_rew_weight;
+  if (s->wtd < (real)cfg->tol) { *rew += 1; done = 1; }
+  return done;
+}
+
 /* AntFlagrunBulletEnv.step after the inner walker step (ant_flagrun_env.py:167-202). */
 static int flagrun_task(hrlo_env* E, int e, env_state* s, calc_t* c, real inner, int done, real* rew, int* switched) {
   const hrl_config* cfg = &E->cfg;
@@ -1433,9 +1440,7 @@ static int step_env(hrlo_env* E, int e, const float* act, real* obs, real* rew, 
       if (kind == HRL_ANT_MAZE) {
         done = maze_task(cfg, s, inner, done, rew);
       } else if (kind == HRL_ANT_MAZE_MJ) {
-        /* ant_maze_mj_env.py:73-77 */
-        *rew = inner * (real)cfg->inner_rew_weight;
-        if (s->wtd < (real)cfg->tol) { *rew += 1; done = 1; }
+        done = maze_mj_task(cfg, s, inner, done, rew);
       } else if (kind == HRL_ANT_FLAGRUN) {
         /* ant_flagrun_env.py:162-204 */
         done = flagrun_task(E, e, s, &c, inner, done, rew, &switched);
@@ -1667,6 +1672,30 @@ int hrlo_maze_task_replay(const hrl_config* cfg, const double* obs28, const doub
   real o[64], rew;
   compose_obs(E, s, &cs, o);
   int done = maze_task(&c, s, (real)inner_rew, inner_done, &rew);
+  for (int i = 0; i < hrlo_obs_dim(&c); i++) obs[i] = o[i];
+  rew_done[0] = rew; rew_done[1] = done;
+  hrlo_destroy(E);
+  return HRL_OK;
+}
+
+/* AntMazeMjEnv.step / _get_obs with a stub inner AntMjEnv step (tests/golden/maze_mj_step.npz): obs29 = MjAnt's
+ * observation (its first two entries are the xy the wall lidar is cast from, ant_maze_mj_env.py:58-59), yaw = the
+ * torso yaw, wtd = robot.walk_target_dist, t_before = self.t on entry (the observation carries t_before * 0.001, :64). */
+int hrlo_maze_mj_task_replay(const hrl_config* cfg, const double* obs29, double yaw, double inner_rew, int inner_done, double wtd,
+                             int t_before, double* obs, double* rew_done) {
+  hrlo_env* E;
+  hrl_config c = *cfg; c.num_envs = 1;
+  if (hrlo_create(&c, &E)) return HRL_E_INVALID;
+  env_state* s = &E->s[0];
+  calc_t cs; memset(&cs, 0, sizeof cs);
+  for (int i = 0; i < 3; i++) { s->pos[i] = (real)obs29[i]; s->vel[i] = (real)obs29[15 + i]; s->ang[i] = (real)obs29[18 + i]; }
+  for (int i = 0; i < 4; i++) s->quat[i] = (real)obs29[3 + i];
+  for (int j = 0; j < 8; j++) { s->q[j] = (real)obs29[7 + j]; s->qd[j] = (real)obs29[21 + j]; }
+  cs.rpy[2] = (real)yaw; cs.wtd = (real)wtd;
+  s->wtd = (real)wtd; s->t = t_before;
+  real o[64], rew;
+  compose_obs(E, s, &cs, o);
+  int done = maze_mj_task(&c, s, (real)inner_rew, inner_done, &rew);
   for (int i = 0; i < hrlo_obs_dim(&c); i++) obs[i] = o[i];
   rew_done[0] = rew; rew_done[1] = done;
   hrlo_destroy(E);

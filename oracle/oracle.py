@@ -64,6 +64,7 @@ def lib(f32=False):
         L.hrlo_maze_target_sensor.restype = None
         L.hrlo_maze_task_replay.argtypes = [C.POINTER(HrlConfig), C.c_void_p, C.c_void_p, d, d, C.c_int, d, C.c_void_p, C.c_int,
                                             C.c_void_p, C.c_void_p]
+        L.hrlo_maze_mj_task_replay.argtypes = [C.POINTER(HrlConfig), C.c_void_p, d, d, C.c_int, d, C.c_int, C.c_void_p, C.c_void_p]
         L.hrlo_flagrun_replay.argtypes = [C.POINTER(HrlConfig), C.c_void_p, C.c_int] + [C.c_void_p] * 7
         L.hrlo_point_state.argtypes = [C.c_void_p] * 4
         L.hrlo_point_state.restype = None

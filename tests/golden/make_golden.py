@@ -327,6 +327,43 @@ def gen_maze_step(rng):
              inner_done=inner_done, wtd=wtd, tid=tid, targets=targets, **res)
 
 
+# --------------------------------------------------------------------------- 8b. AntMazeMj.step task layer
+def gen_maze_mj_step(rng):
+    """Whole `AntMazeMjEnv.step` / `_get_obs` (ant_maze_mj_env.py:57-79) with a stub inner `AntMjEnv.step`: 60-d
+    observation [mj 29 | walls 10 | 0 x 10 | 0 x 10 | t * 0.001], reward inner * weight (+1 inside tol), done."""
+    from hrl_pybullet_envs.envs.ant_maze.ant_maze_mj_env import AntMazeMjEnv
+    M = 300
+    maze = MazeScene(None, 9.8, 0.0165 / 4, 4)
+    mj_obs = f32(rng.uniform(-1, 1, size=(M, 29)))
+    mj_obs[:, 0:2] = f32(rng.uniform((-5, -9), (5, 9), size=(M, 2)))   # the lidar is cast from ant_obs[:2] (:58-59)
+    yaw = f32(rng.uniform(-math.pi, math.pi, size=M))
+    inner_rew = f32(rng.uniform(-2, 2, size=M))
+    inner_done = rng.uniform(size=M) < 0.2
+    wtd = f32(rng.uniform(0.5, 4.0, size=M))
+    t_before = rng.integers(0, 2000, size=M)
+    variants = {"": {}, "_weight": dict(inner_rew_weight=0.5, tol=2.5)}
+    res = {}
+    for tag, kw in variants.items():
+        OBS, REW, DONE, T_AFTER = [], [], [], []
+        for m in range(M):
+            mazemj_mod.AntMjEnv.step = lambda self, a, m=m: (mj_obs[m].copy(), float(inner_rew[m]), bool(inner_done[m]), {})
+            env = AntMazeMjEnv.__new__(AntMazeMjEnv)
+            env.t = int(t_before[m]); env.debug = 0; env.inner_rew_weight = 0; env.tol = 1.5
+            env.n_bins = 10; env.sensor_span = 2 * np.pi; env.sensor_range = 5.0
+            for k, v in kw.items():
+                setattr(env, k, v)
+            env.scene = maze
+            env.robot = NS(walk_target_dist=float(wtd[m]))
+            env.robot_body = NS(pose=lambda m=m: pose_ns([mj_obs[m, 0], mj_obs[m, 1], 0.5], [0, 0, float(yaw[m])]))
+            obs, rew, done, info = env.step(np.zeros(8))
+            OBS.append(obs); REW.append(rew); DONE.append(done); T_AFTER.append(env.t)
+        res.update({"obs" + tag: np.array(OBS, dtype=np.float64), "rew" + tag: np.array(REW, dtype=np.float64),
+                    "done" + tag: np.array(DONE), "t_after" + tag: np.array(T_AFTER)})
+    del mazemj_mod.AntMjEnv.step
+    np.savez_compressed(os.path.join(HERE, "maze_mj_step.npz"), mj_obs=mj_obs, yaw=yaw, inner_rew=inner_rew, inner_done=inner_done,
+                        wtd=wtd, t_before=t_before, targets=np.array(mazemj_mod._targets, dtype=np.float64), **res)
+
+
 # --------------------------------------------------------------------------- 9. Flagrun.step sequence
 def gen_flagrun_step(rng):
     """Drive the reference's Flagrun step logic with a scripted sequence of walk_target_dist
@@ -436,6 +473,7 @@ if __name__ == "__main__":
     gen_flagrun_step(rng)
     gen_robots(rng)
     gen_registry()
+    gen_maze_mj_step(np.random.default_rng(20261020))   # added in round 2 with its own generator (files above unchanged)
     for fn in sorted(os.listdir(HERE)):
         if fn.endswith((".npz", ".json")):
             print(fn, os.path.getsize(os.path.join(HERE, fn)))

@@ -183,6 +183,29 @@ def test_maze_step_task_layer(golden, tag):
         assert rd[0] == pytest.approx(g["rew" + tag][m], abs=1e-12) and bool(rd[1]) == bool(g["done" + tag][m])
 
 
+# ---------------------------------------------------------------- whole MazeMj step task layer (maze_mj_step.npz)
+@pytest.mark.parametrize("tag", ["", "_weight"])
+def test_maze_mj_step_task_layer(golden, tag):
+    """AntMazeMjEnv.step / _get_obs with a stub inner AntMjEnv step (ant_maze_mj_env.py:57-79): the 60-d observation
+    [mj 29 | walls 10 | 0 x 10 | 0 x 10 | t * 0.001 with t taken BEFORE the increment], reward and done."""
+    g = golden("maze_mj_step.npz")
+    L = O.lib()
+    cfg = O.default_config(K.HRL_ANT_MAZE_MJ, 1)
+    for k, v in {"": {}, "_weight": {"inner_rew_weight": 0.5, "tol": 2.5}}[tag].items():
+        setattr(cfg, k, v)
+    assert L.hrlo_obs_dim(O.C.byref(cfg)) == 60
+    assert np.array_equal(g["targets"], np.array([list(cfg.targets[i]) for i in range(cfg.n_targets)]))   # ant_maze_mj_env.py:13-14
+    for m in range(len(g["mj_obs"])):
+        obs = np.zeros(60); rd = np.zeros(2)
+        L.hrlo_maze_mj_task_replay(O.C.byref(cfg), O._p(np.ascontiguousarray(g["mj_obs"][m].astype(np.float64))), float(g["yaw"][m]),
+                                   float(g["inner_rew"][m]), int(g["inner_done"][m]), float(g["wtd"][m]), int(g["t_before"][m]),
+                                   O._p(obs), O._p(rd))
+        np.testing.assert_allclose(obs, g["obs" + tag][m], rtol=0, atol=1e-12)
+        assert rd[0] == pytest.approx(g["rew" + tag][m], abs=1e-12) and bool(rd[1]) == bool(g["done" + tag][m])
+        assert g["t_after" + tag][m] == g["t_before"][m] + 1
+    assert g["done"].any() and not g["done"].all() and (g["rew"] == 1).any()
+
+
 # ---------------------------------------------------------------- Flagrun step sequences (flagrun_step.npz)
 @pytest.mark.parametrize("tag", ["a", "b", "c"])
 def test_flagrun_step_sequence(golden, tag):

@@ -34,6 +34,13 @@ def regions():
              ("integrate", "back to physical velocities")]
     pos = [(n, L(ant, p)) for n, p in marks] + [(None, len(ant) + 1)]
     out = [("hrl_ant.cuh", lo, hi - 1, n) for (n, lo), (_, hi) in zip(pos, pos[1:]) if n]
+    wide = open(os.path.join(ROOT, "hrl_pybullet_envs_b200/csrc/hrl_ant_wide.cuh")).read().split("\n")
+    wmarks = [("w_contact_helpers", "int add_cand_w("), ("w_dynamics", "void leg_dynamics_w("), ("w_emit_row", "void emit_row_w("),
+              ("w_pgs_helpers", "struct RowW"), (None, "void ant_substep_w("), ("w_contacts_detect", "contacts: the leg's sphere slots"),
+              ("w_dynamics_call", "smooth dynamics (replicated"), ("w_rows_build", "constraint rows: counts, visit positions; sub-lane"),
+              ("w_pgs", "projected Gauss-Seidel, Bullet row order (see"), ("w_integrate", "back to physical velocities, clamp, integrate (as")]
+    wpos = [(n, L(wide, p)) for n, p in wmarks] + [(None, len(wide) + 1)]
+    out += [("hrl_ant_wide.cuh", lo, hi - 1, n) for (n, lo), (_, hi) in zip(wpos, wpos[1:]) if n]
     out += [("hrl_math.cuh", 1, 48, "math_helpers"), ("hrl_math.cuh", 49, 200, "rng"), ("hrl_sensors.cuh", 1, 400, "sensors")]
     a, b, c, d = L(cu, "// ---- load ----"), L(cu, "// ---- task layer: observation"), L(cu, "// ---- store ----"), L(cu, "// PointGather (point_bot.py")
     out += [("hrl_b200.cu", a - 20, b - 1, "load_physics_loop"), ("hrl_b200.cu", b, c - 1, "task_layer"), ("hrl_b200.cu", c, d, "store")]
@@ -42,7 +49,7 @@ def regions():
 
 def main():
     rep = sys.argv[1]
-    tag = sys.argv[2] if len(sys.argv) > 2 else "ant_env_kernelILi0"
+    tag = sys.argv[2] if len(sys.argv) > 2 else "ant_env_kernelILi0ELi1E"
     so = os.path.join(ROOT, "hrl_pybullet_envs_b200", "libhrl_b200.so")
     with tempfile.TemporaryDirectory() as tmp:
         subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
