@@ -413,7 +413,13 @@ def run_ours(args):
                   "peak_at_sampled_clock": roofline.fp32_peak_tflops(sm_clk),
                   "algorithmic_flop_per_env_step": flops, "contacts_per_substep": stats["contacts_per_substep"],
                   "limit_rows_per_substep": stats["limit_rows_per_substep"],
-                  "model": "instrumented: coefficients fitted to an operation count of the f64 oracle (tools/count_oracle_flops.py)"}
+                  "model": "minimum of the kernel's own formulation (block-arrow elimination, hrl_pybullet_envs_b200/roofline.py); "
+                           "oracle_counted_flop_per_env_step is the instrumented count of the f64 scalar restatement "
+                           "(13-link ABA + one ABA impulse response per row) under the same contact statistics"}
+            om = profile_json("r2_oracle_flop_model.json")
+            if om:
+                rows_ = 3.0 * stats["contacts_per_substep"] + stats["limit_rows_per_substep"]
+                fp["oracle_counted_flop_per_env_step"] = 4 * (om["per_env_substep"] + rows_ * (om["per_row"] + 5 * om["per_row_iteration"])) + om["per_env_step_task_layer"]
             if prof.get("executed_fp32_flop_per_launch"):
                 # executed thread-level fp32 operations of the committed ncu capture (same regime: settled ants, same batch)
                 ex = prof["executed_fp32_flop_per_launch"] / prof.get("envs_per_launch", N)

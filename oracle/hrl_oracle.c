@@ -27,7 +27,16 @@
 
 #include "../include/hrl_b200.h"
 
-#ifdef HRLO_F32
+#if defined(HRLO_COUNT) /* C++ build with a counting `real` (oracle/flop_counter.hpp, tools/count_oracle_flops.py) */
+typedef creal real;
+#define R_SQRT c_sqrt
+#define R_SIN c_sin
+#define R_COS c_cos
+#define R_ATAN2 c_atan2
+#define R_ASIN c_asin
+#define R_FABS c_fabs
+#define R_FLOOR c_floor
+#elif defined(HRLO_F32)
 typedef float real;
 #define R_SQRT sqrtf
 #define R_SIN sinf
@@ -972,7 +981,7 @@ int hrlo_random_on_plane_replay(double world_x, double world_y, double spacing, 
   c.world_size[0] = (float)world_x; c.world_size[1] = (float)world_y; c.robot_object_spacing = (float)spacing;
   real o[2];
   int used = random_on_plane(&c, (real)ax, (real)ay, 0, 0, 0, 0, 0, uniforms, o);
-  out_xy[0] = o[0]; out_xy[1] = o[1];
+  out_xy[0] = (double)o[0]; out_xy[1] = (double)o[1];
   return 2 * used;
 }
 
@@ -1649,9 +1658,9 @@ int hrlo_gather_task_replay(const hrl_config* cfg, const double* base, int nbase
   real b[32], o[64], rew, info[4]; int done;
   for (int i = 0; i < nbase; i++) b[i] = (real)base[i];
   gather_task(E, 0, s, b, nbase, (real)xyz[2], can_die, (real)yaw, uniforms, used, NULL, o, &rew, &done, info);
-  for (int i = 0; i < nbase + food_obs_dim(&c); i++) obs[i] = o[i];
-  for (int i = 0; i < HRL_MAX_ITEMS; i++) { items_xy[2 * i] = s->items[i][0]; items_xy[2 * i + 1] = s->items[i][1]; }
-  rew_done_info[0] = rew; rew_done_info[1] = done; rew_done_info[2] = info[0]; rew_done_info[3] = info[1];
+  for (int i = 0; i < nbase + food_obs_dim(&c); i++) obs[i] = (double)o[i];
+  for (int i = 0; i < HRL_MAX_ITEMS; i++) { items_xy[2 * i] = (double)s->items[i][0]; items_xy[2 * i + 1] = (double)s->items[i][1]; }
+  rew_done_info[0] = (double)rew; rew_done_info[1] = done; rew_done_info[2] = (double)info[0]; rew_done_info[3] = (double)info[1];
   hrlo_destroy(E);
   return HRL_OK;
 }
@@ -1672,8 +1681,8 @@ int hrlo_maze_task_replay(const hrl_config* cfg, const double* obs28, const doub
   real o[64], rew;
   compose_obs(E, s, &cs, o);
   int done = maze_task(&c, s, (real)inner_rew, inner_done, &rew);
-  for (int i = 0; i < hrlo_obs_dim(&c); i++) obs[i] = o[i];
-  rew_done[0] = rew; rew_done[1] = done;
+  for (int i = 0; i < hrlo_obs_dim(&c); i++) obs[i] = (double)o[i];
+  rew_done[0] = (double)rew; rew_done[1] = done;
   hrlo_destroy(E);
   return HRL_OK;
 }
@@ -1696,8 +1705,8 @@ int hrlo_maze_mj_task_replay(const hrl_config* cfg, const double* obs29, double 
   real o[64], rew;
   compose_obs(E, s, &cs, o);
   int done = maze_mj_task(&c, s, (real)inner_rew, inner_done, &rew);
-  for (int i = 0; i < hrlo_obs_dim(&c); i++) obs[i] = o[i];
-  rew_done[0] = rew; rew_done[1] = done;
+  for (int i = 0; i < hrlo_obs_dim(&c); i++) obs[i] = (double)o[i];
+  rew_done[0] = (double)rew; rew_done[1] = done;
   hrlo_destroy(E);
   return HRL_OK;
 }
@@ -1720,7 +1729,7 @@ int hrlo_flagrun_replay(const hrl_config* cfg, const double* goals, int n_steps,
     real r;
     int sw = 0;
     int d = flagrun_task(E, 0, s, &cs, (real)inner_r[i], 0, &r, &sw);
-    rew[i] = r; done_out[i] = d; target[2 * i] = s->target[0]; target[2 * i + 1] = s->target[1];
+    rew[i] = (double)r; done_out[i] = d; target[2 * i] = (double)s->target[0]; target[2 * i + 1] = (double)s->target[1];
     since[i] = s->since; rewarded[i] = s->rewarded;
     if (d) { i++; break; }
   }
@@ -1733,7 +1742,7 @@ void hrlo_point_state(const double xyz[3], const double rpy[3], const double vel
   real a[3] = {(real)xyz[0], (real)xyz[1], (real)xyz[2]}, r[3] = {(real)rpy[0], (real)rpy[1], (real)rpy[2]};
   real v[3] = {(real)vel[0], (real)vel[1], (real)vel[2]}, o[8];
   point_state_general(a, r, v, 1, o);
-  for (int i = 0; i < 8; i++) out8[i] = o[i];
+  for (int i = 0; i < 8; i++) out8[i] = (double)o[i];
 }
 void hrlo_point_force(const hrl_config* cfg, const double act[2], double f[3]) {
   double nn = sqrt(act[0] * act[0] + act[1] * act[1]); /* point_bot.py:29 */
@@ -1767,6 +1776,6 @@ int hrlo_free_accel(hrlo_env* E, int e, const real* tau, real* udot) {
 }
 void hrlo_stats(hrlo_env* E, double out[3]) { out[0] = E->n_contacts; out[1] = E->n_limit_rows; out[2] = E->n_substeps; }
 void hrlo_rng_u4(uint64_t seed, uint32_t env, uint32_t stream, uint32_t draw, uint32_t sub, double* u) {
-  real r[4]; rng_u4(seed, env, stream, draw, sub, r); for (int i = 0; i < 4; i++) u[i] = r[i];
+  real r[4]; rng_u4(seed, env, stream, draw, sub, r); for (int i = 0; i < 4; i++) u[i] = (double)r[i];
 }
-void hrlo_flag_goal(const hrl_config* cfg, int episode, int j, double* g) { real r[2]; flag_goal(cfg, episode, j, 0, r); g[0] = r[0]; g[1] = r[1]; }
+void hrlo_flag_goal(const hrl_config* cfg, int episode, int j, double* g) { real r[2]; flag_goal(cfg, episode, j, 0, r); g[0] = (double)r[0]; g[1] = (double)r[1]; }

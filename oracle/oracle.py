@@ -25,11 +25,14 @@ def build(force=False):
     return out
 
 
-def lib(f32=False):
-    key = bool(f32)
+def lib(f32=False, count=False):
+    """count=True: the C++ build whose `real` counts its arithmetic (oracle/flop_counter.hpp, `make count`)."""
+    key = "count" if count else bool(f32)
     if key not in _LIBS:
         build()
-        path = os.path.join(_HERE, "_build", "libhrl_oracle_f32.so" if f32 else "libhrl_oracle.so")
+        if count:
+            subprocess.check_call(["make", "-C", _HERE, "-s", "count"], stdout=subprocess.DEVNULL)
+        path = os.path.join(_HERE, "_build", "libhrl_oracle_count.so" if count else ("libhrl_oracle_f32.so" if f32 else "libhrl_oracle.so"))
         L = C.CDLL(path)
         L.hrlo_default_config.argtypes = [C.c_int32, C.c_int32, C.POINTER(HrlConfig)]
         L.hrlo_create.argtypes = [C.POINTER(HrlConfig), C.POINTER(C.c_void_p)]
@@ -95,8 +98,8 @@ def _p(a):
 class OracleVecEnv:
     """N envs stepped on the host by the C oracle; same call shapes as the CUDA VecEnv."""
 
-    def __init__(self, cfg, f32=False, threads=1):
-        self.L = lib(f32)
+    def __init__(self, cfg, f32=False, threads=1, count=False):
+        self.L = lib(f32, count)
         self.cfg = cfg.copy()
         self.real = np.float32 if f32 else np.float64
         self.h = C.c_void_p()
