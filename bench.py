@@ -390,9 +390,9 @@ def run_ours(args):
                        "parity": "task layer pinned on reference-executed fixtures; physics vs our own f64 oracle port only "
                                  "(pybullet absent: parity unpinned against real Bullet)"},
             "e2e": {"value": total_envs * K / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": N * A * 4, "d2h_bytes_per_step": N * (D * 4 + 4 + 1 + 16),
+                    "h2d_bytes_per_step": N * A * 4, "d2h_bytes_per_step": N * (D * 4 + 4 + 1),
                     "api": "VecEnv.step(numpy) -> hrl_step_host, zero-copy mode: the kernel reads the actions from and writes "
-                           "obs/rew/done/info to pinned host memory over PCIe; the host polls a completion word the last CTA publishes",
+                           "obs/rew/done to pinned host memory over PCIe (info stays on the device until somebody reads it); the host polls a completion word the last CTA publishes",
                     "segments": "median of %d segments of %d steps, wall clock, slowest rank" % (E2E_SEGMENTS, K),
                     "segment_values": [total_envs * K / s for s in e2e_modes["zerocopy"]],
                     "value_copy_mode": total_envs * K / (e2e_copy_ms * 1e-3),

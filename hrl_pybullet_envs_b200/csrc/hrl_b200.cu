@@ -1362,7 +1362,8 @@ static void* mapped_alias(hrl_handle* h, const void* p, bool cache = true) {
       if (h->alias_key[i] == p) return h->alias_val[i];
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-  void* d = (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
+  // pinned host memory: its device alias; device memory (a caller may keep `info` on the device): the pointer itself
+  void* d = (a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeDevice) ? a.devicePointer : nullptr;
   if (d && cache) {
     if (h->alias_n == 12) h->alias_n = 0;  // tiny ring: evict everything
     h->alias_key[h->alias_n] = p; h->alias_val[h->alias_n] = d; h->alias_n++;
@@ -1411,6 +1412,11 @@ int hrl_step_host(hrl_handle* h, const float* h_actions, float* h_obs, float* h_
   if (rc) return rc;
   size_t off_rew, off_info, off_done, total;
   hrl_host_layout(&h->cfg, &off_rew, &off_info, &off_done, &total);
+  const bool info_on_device = h_info && mapped_alias(h, h_info) == (void*)h_info;   // device pointer: no copy wanted
+  if (info_on_device) {
+    CK(cudaMemcpyAsync(h_info, h->s_info, N * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    h_info = nullptr;
+  }
   if (h_info && (char*)h_rew == (char*)h_obs + off_rew && (char*)h_info == (char*)h_obs + off_info &&
       (char*)h_done == (char*)h_obs + off_done) {
     CK(cudaMemcpyAsync(h_obs, h->s_obs, off_done + N, cudaMemcpyDeviceToHost, s));  // packed layout: one copy

@@ -184,6 +184,8 @@ int hrl_step_host(hrl_handle* h, const float* h_actions, float* h_obs, float* h_
  *   HRL_HOST_ZEROCOPY  the output buffers must be pinned: the kernel writes them over PCIe while
  *                      it computes (transfers overlap the step), sync;
  *   HRL_HOST_AUTO      zero-copy when all output buffers are pinned, else copy (default).
+ * h_info may also be a DEVICE pointer: the per-step info columns then stay on the device (16 of the 205 bytes per env the
+ * host path would otherwise move) and the caller fetches them only when somebody looks (VecEnv does).
  * In the last two modes a pinned action array is read in place over PCIe; a pageable one (the
  * array a gym-style caller hands over) is copied H2D first - it is asked afresh on every call.
  * The handle caches which host pointers are pinned; calling hrl_set_host_mode (any mode) clears

@@ -737,3 +737,70 @@ def test_ragged_batch_sizes(env_id, N):
         assert same.mean() > 0.9
         live = same & ~do
         assert np.abs(canary[:N].cpu().numpy()[live][:, :8] - oo[live][:, :8]).max(initial=0) < 2e-2
+
+
+# ------------------------------------------------------------------ host-side argument handling (round-1 advice)
+def test_flagrun_seed_kwarg_seeds_the_shared_goal_stream():
+    """The reference's ctor kwarg `seed` (ant_flagrun_env.py:16,39) seeds the goal stream shared by all envs: different
+    seeds give different goals, the same seed the same ones, and all envs of a batch chase the same goal sequence."""
+    from hrl_pybullet_envs_b200 import VecEnv, make
+    N = 32
+    goals = {}
+    for s in (5, 5, 6, None):
+        e = VecEnv("AntFlagrunBulletEnv-v0", N, seed=s)
+        e.reset()
+        goals.setdefault(s, []).append(e.goal.clone())
+        assert (e.goal == e.goal[0]).all()                       # one stream for every env (mpi_common_rand)
+    assert torch.equal(goals[5][0], goals[5][1]) and not torch.equal(goals[5][0], goals[6][0])
+    assert not torch.equal(goals[None][0], goals[5][0])           # default stream (seed 123)
+    d = VecEnv("AntFlagrunBulletEnv-v0", N, seed=123); d.reset()
+    assert torch.equal(d.goal, goals[None][0])
+    # env_seed re-keys the per-env streams (joint noise) and leaves the goals alone
+    a = VecEnv("AntFlagrunBulletEnv-v0", N, seed=5, env_seed=1); b = VecEnv("AntFlagrunBulletEnv-v0", N, seed=5, env_seed=2)
+    oa = a.reset().clone(); ob = b.reset().clone()
+    assert torch.equal(a.goal, b.goal) and not torch.equal(oa, ob)
+    # the gym-style shim forwards the kwarg; repeated create_targets() draw fresh goals (ant_flagrun_env.py:91-96)
+    g1 = make("AntFlagrunBulletEnv-v0", seed=5); g1.reset()
+    assert g1.goal == tuple(float(x) for x in goals[5][0][0])
+    m = VecEnv("AntFlagrunBulletEnv-v0", 4, seed=5, manual_goal_creation=True); m.reset()
+    m.create_targets(3); m.next_target(); first = m.goal.clone()
+    m.create_targets(3); m.next_target()
+    assert not torch.equal(first, m.goal)
+
+
+def test_host_side_validation():
+    from hrl_pybullet_envs_b200 import VecEnv
+    e = VecEnv("AntMazeBulletEnv-v0", 16, seed=1)
+    e.reset()
+    with pytest.raises(KeyError):
+        VecEnv("AntMazeBulletEnv-v0", 16, config_overrides={"solver_iter": 3})      # misspelled field
+    with pytest.raises(ValueError):
+        e.reset(mask=torch.ones(8, dtype=torch.uint8))                              # short mask
+    with pytest.raises(ValueError):
+        e.step(torch.zeros(8, 16, device="cuda"))                                   # right numel, wrong shape
+    with pytest.raises(ValueError):
+        e.step(np.zeros((16, 4), np.float32))
+    # a masked reset returns a consistent batch: rows outside the mask show the CURRENT observation of their env
+    e.step(torch.rand(16, 8, device="cuda") * 2 - 1)
+    cur = e.observe().clone()
+    mask = torch.zeros(16, dtype=torch.uint8); mask[:4] = 1
+    out = e.reset(mask)
+    assert torch.equal(out[4:], cur[4:]) and not torch.equal(out[:4], cur[:4])
+    # the caller's current device is left alone
+    assert torch.cuda.current_device() == 0
+
+
+def test_cuda_graph_rollout_matches_stepping():
+    """VecEnv.capture_rollout: T steps as ONE graph launch == T individual steps, bit for bit."""
+    from hrl_pybullet_envs_b200 import VecEnv
+    N, T = 128, 8
+    a = VecEnv("AntGatherBulletEnv-v0", N, seed=3); b = VecEnv("AntGatherBulletEnv-v0", N, seed=3)
+    a.reset(); b.reset()
+    acts = (torch.rand(T, N, 8, device="cuda") * 2 - 1).contiguous()
+    fa, ia = a.get_state()
+    graph, buf = b.capture_rollout(acts)          # (the capture itself steps nothing: work is only recorded)
+    b.set_state(fa, ia)
+    graph.replay(); torch.cuda.synchronize()
+    for t in range(T):
+        o, r, d, _ = a.step(acts[t])
+        assert torch.equal(o, buf.obs[t + 1]) and torch.equal(r, buf.rew[t]) and torch.equal(d, buf.done[t])
