@@ -1255,7 +1255,7 @@ int hrl_create(const hrl_config* cfg, int32_t device, hrl_handle** out) {
 #endif
   if (cudaHostAlloc((void**)&h->h_flag, 64, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); h->h_flag = nullptr; }
   else *h->h_flag = 0;
-  ALLOC(h->d_bounds, 7 * 4 * sizeof(float));
+  ALLOC(h->d_bounds, 32 * sizeof(float));  // 7 x 4 bound lines (+ pad: the kernels fetch them with one 32-lane load)
   ALLOC(h->s_act, N * h->A * sizeof(float));
   {
     size_t off_rew, off_info, off_done, total;
@@ -1273,7 +1273,8 @@ int hrl_create(const hrl_config* cfg, int32_t device, hrl_handle** out) {
     cudaError_t _e = (call);                                                    \
     if (_e != cudaSuccess) { hrl_destroy(h); return cuda_fail(_e, #call); }     \
   } while (0)
-  float b[28];
+  float b[32];
+  memset(b, 0, sizeof b);
   h->n_lines = scene_bounds(cfg, b);
   CKH(cudaMemcpy(h->d_bounds, b, sizeof b, cudaMemcpyHostToDevice));
   // opt in to the dynamic shared memory the ant kernels need; they live in shared memory and registers (hardly any
@@ -1501,7 +1502,7 @@ int hrl_gather_sensor(int32_t M, int32_t n_bins, float sensor_range, float senso
 
 int hrl_sense_walls(int32_t M, int32_t n_bins, float span, float range, int32_t n_lines, const float* d_bounds,
                     const float* d_xy, const float* d_yaw, float* d_out, void* stream) {
-  if (M < 0 || n_bins < 1 || n_lines < 0 || !d_bounds || !d_xy || !d_yaw || !d_out)
+  if (M < 0 || n_bins < 1 || n_bins > HRL_MAX_BINS || n_lines < 0 || !d_bounds || !d_xy || !d_yaw || !d_out)
     return set_err(HRL_E_INVALID, "bad argument to hrl_sense_walls");
   if (M == 0) return HRL_OK;
   const int T = 128, G = (M * n_bins + T - 1) / T;
