@@ -12,9 +12,11 @@ print('   value %.4g  ms/step %.4f  b2b %.4g  e2e %.4g  clocks %s' % (d['value']
 print('   per-rank mean us', d['config']['per_rank_step_us']['mean'], 'max', d['config']['per_rank_step_us']['max'], 'slowest', d['config']['per_rank_step_us']['slowest_rank'])"
 }
 run AntGather 20 5 drv
-run AntGather 20 5 drv2
-run AntGather 1000 200 long
 run AntMaze 20 5 drv
-run AntMaze 500 200 long
 run AntFlagrun 20 5 drv
-run AntFlagrun 500 200 long
+if [ -z "$SHORT" ]; then
+  run AntGather 20 5 drv2
+  run AntGather 1000 200 long
+  run AntMaze 500 200 long
+  run AntFlagrun 500 200 long
+fi
