@@ -164,9 +164,15 @@ def apply_kwargs(cfg, kind, kw):
             cfg.sensor_range = float(kw.pop("sensor_range"))
         if "manual_goal_creation" in kw:   # ant_flagrun_env.py:150-153: reset() creates no goals; VecEnv.set_target / create_targets
             cfg.flag_manual_goals = int(bool(kw.pop("manual_goal_creation")))
-        if "enclosed" in kw and kw["enclosed"] is not True:
-            raise NotImplementedError(_UNSUPPORTED % ("enclosed", kw["enclosed"]))
-        kw.pop("enclosed", None)
+        enclosed = bool(kw.pop("enclosed", True))
+        if not (enclosed or cfg.flag_use_sensor):
+            # ant_flagrun_env.py:59-69: neither enclosed nor sensing -> the stock pybullet_envs stadium scene [3P-MEM]:
+            # an open ground plane at z = 0 (stadium_no_collision.sdf), no walls.  Its three SDF bodies sit at the origin
+            # and join the robot's parts like the arena bodies do (quirk Q1): 3 scene parts, xy sum (0, 0) [3P-MEM L].
+            cfg.has_walls = 0
+            cfg.ground_z = 0.0
+            cfg.n_scene_parts = 3
+            cfg.scene_parts_sum[0] = cfg.scene_parts_sum[1] = 0.0
         if cfg.flag_max_targets > 127:
             raise ValueError("max_targets must be <= 127")
     if kw:

@@ -83,8 +83,12 @@ def test_kwargs_mapping():
     g = _cabi.default_config(K.HRL_ANT_FLAGRUN, 1)
     K.apply_kwargs(g, K.HRL_ANT_FLAGRUN, dict(manual_goal_creation=True))   # ant_flagrun_env.py:150-153
     assert g.flag_manual_goals == 1
-    with pytest.raises(NotImplementedError):                             # the pybullet_envs stadium scene is not built
-        K.apply_kwargs(_cabi.default_config(K.HRL_ANT_FLAGRUN, 1), K.HRL_ANT_FLAGRUN, dict(enclosed=False))
+    o = _cabi.default_config(K.HRL_ANT_FLAGRUN, 1)                       # ant_flagrun_env.py:59-69: the open stadium scene
+    K.apply_kwargs(o, K.HRL_ANT_FLAGRUN, dict(enclosed=False))
+    assert (o.has_walls, o.ground_z, o.n_scene_parts) == (0, 0.0, 3)
+    o2 = _cabi.default_config(K.HRL_ANT_FLAGRUN, 1)                      # use_sensor keeps the walled arena (:60)
+    K.apply_kwargs(o2, K.HRL_ANT_FLAGRUN, dict(enclosed=False, use_sensor=True))
+    assert o2.has_walls == 1
     m = _cabi.default_config(K.HRL_ANT_MAZE, 1)
     K.apply_kwargs(m, K.HRL_ANT_MAZE, dict(targets=([1, 2], [3, 4]), tol=2.0, target_encoding=1))
     assert m.n_targets == 2 and m.targets[1][0] == 3.0 and m.tol == 2.0 and m.target_encoding == 1

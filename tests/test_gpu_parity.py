@@ -599,6 +599,7 @@ KWARG_CASES = [
     ("AntFlagrunBulletEnv-v0", dict(manual_goal_creation=True)),            # ant_flagrun_env.py:150-153: no goals drawn at reset
     ("AntFlagrunBulletEnv-v0", dict(switch_flag_on_collision=False, timeout=15, max_targets=3, tolerance=2.5)),
     ("AntFlagrunBulletEnv-v0", dict(max_targets=0, max_target_dist=4.0, tolerance=1.5, timeout=10)),  # create_close_target :80-89
+    ("AntFlagrunBulletEnv-v0", dict(enclosed=False)),                       # ant_flagrun_env.py:59-69: open stadium ground, no walls
 ]
 
 
