@@ -53,9 +53,11 @@
 #define HRL_CAND_F 8
 #define HRL_SMEM_FLOATS_PER_WARP (HRL_ROWS_FLOATS_PER_WARP + HRL_LAM_FLOATS_PER_WARP + HRL_MAXC * HRL_CAND_F * 32)
 
-// food / poison cube colliders (hrl_config.item_contacts): per-warp scratch [EPW][16] (x, y) + [EPW] 64-bit words
-// holding 16 4-bit contact-point counters (<= 13 spheres can touch one cube)
-#define HRL_ITEM_SCRATCH_FLOATS (HRL_EPW * 16 * 2 + HRL_EPW * 2)
+// food / poison cube colliders (hrl_config.item_contacts): per-warp scratch [EPW][16] (x, y) + [EPW][2] 64-bit words
+// holding 16 8-bit contact-point counters (13 spheres + 12 capsule cylinders can touch one cube)
+#define HRL_ITEM_SCRATCH_FLOATS (HRL_EPW * 16 * 2 + HRL_EPW * 4)
+#define HRL_TOUCH_ADD(itouch, gi) atomicAdd((itouch) + ((gi) >> 3), 1ull << (8 * ((gi) & 7)))
+#define HRL_TOUCH_GET(itouch, gi) ((int)(((itouch)[(gi) >> 3] >> (8 * ((gi) & 7))) & 255ull))
 
 struct AntLane {
   // replicated in the 4 lanes of an env
@@ -294,6 +296,82 @@ __device__ __noinline__ int capsules_vs_box_edges(V3 O, V3 rh, V3 r_ank, V3 r_ti
   return nC;
 }
 
+// Food / poison cubes: the CYLINDER part of one leg's three capsules against the candidate cubes (the end-spheres only
+// cover contacts at a capsule end; a leg lying across a cube's edge touches it in between).  Same algorithm and order as
+// the oracle (capsule_interior_vs_box, detect_contacts): cubes in index order, capsules foot, aux, leg; the closest
+// point of the segment's interior is bracketed by 24 bisection steps on the (monotone) derivative of the squared
+// point-box distance; normal and distance there are those of a sphere of the capsule radius.  Candidate (slot, field)
+// lives at cbase[(slot * HRL_CAND_F + field) * stride]; slots slot0, slot0 + 1, ... are filled while < HRL_MAXC.
+// Returns the number of contact points found (stored or not).  Rare: out of line.
+__device__ __forceinline__ float seg_box_grad(const float a[3], const float d[3], float h, float t) {
+  float g = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const float x = fmaf(t, d[i], a[i]);
+    const float e = x > h ? x - h : (x < -h ? x + h : 0.f);
+    g = fmaf(e, d[i], g);
+  }
+  return g;
+}
+__device__ __noinline__ int capsules_vs_cubes(V3 O, V3 rh, V3 r_ank, V3 r_tip, unsigned imask, const float* __restrict__ ixy, float half,
+                                              float iz, float margin, float* __restrict__ cbase, int stride, int slot0,
+                                              unsigned long long* itouch, bool count_touch) {
+  int n = 0;
+  const float rr = half + ant::R_CAPS + margin;
+  for (unsigned m = imask; m; m &= m - 1) {
+    const int gi = __ffs(m) - 1;
+    const float bx = ixy[2 * gi] - O.x, by = ixy[2 * gi + 1] - O.y, bz = iz - O.z;  // cube centre relative to the torso origin
+#pragma unroll 1
+    for (int cap = 0; cap < 3; cap++) {
+      const V3 A = cap == 0 ? r_ank : (cap == 1 ? rh : mk(0.f, 0.f, 0.f));
+      const V3 B = cap == 0 ? r_tip : (cap == 1 ? r_ank : rh);
+      if (bx < fminf(A.x, B.x) - rr || bx > fmaxf(A.x, B.x) + rr || by < fminf(A.y, B.y) - rr || by > fmaxf(A.y, B.y) + rr) continue;
+      const float a[3] = {A.x - bx, A.y - by, A.z - bz}, d[3] = {B.x - A.x, B.y - A.y, B.z - A.z};   // relative to the cube centre
+      if (!(seg_box_grad(a, d, half, 0.f) < 0.f && seg_box_grad(a, d, half, 1.f) > 0.f)) continue;  // minimum at an end: the spheres' business
+      float lo = 0.f, hi = 1.f;
+#pragma unroll 1
+      for (int it = 0; it < 24; it++) {
+        const float mid = 0.5f * (lo + hi);
+        if (seg_box_grad(a, d, half, mid) < 0.f) lo = mid; else hi = mid;
+      }
+      const float t = 0.5f * (lo + hi);
+      const float q[3] = {fmaf(t, d[0], a[0]), fmaf(t, d[1], a[1]), fmaf(t, d[2], a[2])};
+      float e[3];
+      bool inside = true;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        e[i] = q[i] > half ? q[i] - half : (q[i] < -half ? q[i] + half : 0.f);
+        inside = inside && e[i] == 0.f;
+      }
+      V3 nrm; float dist;
+      if (!inside) {
+        const float len = sqrtf(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+        nrm = mk(e[0] / len, e[1] / len, e[2] / len); dist = len - ant::R_CAPS;
+      } else {  // the segment enters the cube: exit through the nearest face (as sphere_vs_aabb_inl)
+        float best = 1e30f; int bi = 0; float bs = 1.f;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          const float dl = q[i] + half, dh = half - q[i];
+          if (dl < best) { best = dl; bi = i; bs = -1.f; }
+          if (dh < best) { best = dh; bi = i; bs = 1.f; }
+        }
+        nrm = mk(bi == 0 ? bs : 0.f, bi == 1 ? bs : 0.f, bi == 2 ? bs : 0.f); dist = -best - ant::R_CAPS;
+      }
+      if (!(dist < margin)) continue;
+      if (count_touch) HRL_TOUCH_ADD(itouch, gi);
+      const int slot = slot0 + n;
+      n++;
+      if (slot < HRL_MAXC) {
+        float* c = cbase + slot * HRL_CAND_F * stride;
+        c[0] = q[0] + bx - ant::R_CAPS * nrm.x; c[stride] = q[1] + by - ant::R_CAPS * nrm.y; c[2 * stride] = q[2] + bz - ant::R_CAPS * nrm.z;
+        c[3 * stride] = nrm.x; c[4 * stride] = nrm.y; c[5 * stride] = nrm.z;
+        c[6 * stride] = dist; c[7 * stride] = (float)(2 - cap) + 4.f;   // link class (foot 2, aux 1, leg 0) + 4: cube friction
+      }
+    }
+  }
+  return n;
+}
+
 // Whiten one constraint row of leg k and store it at visit position `pos` of this env's row buffer.
 //   Jb~ = JB - K [j1 j2]^T (leg eliminated), z = L^-1 Jb~, y = Ll^-1 [j1 j2]^T, diag = |z|^2 + |y|^2.
 __device__ __forceinline__ void emit_row(float4* __restrict__ rb, int pos, int k,
@@ -424,7 +502,7 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
     float* ixy = nullptr;
     unsigned long long* itouch = nullptr;
     if (ITEMS && P.item_contacts) {
-      ixy = iscr + es * 32; itouch = reinterpret_cast<unsigned long long*>(iscr + HRL_EPW * 32) + es;
+      ixy = iscr + es * 32; itouch = reinterpret_cast<unsigned long long*>(iscr + HRL_EPW * 32) + 2 * es;
       const float reach = 1.1314f + 1.4143f * (P.item_half + ant::R_CAPS + P.margin);
 #pragma unroll
       for (int i = 0; i < 4; i++) {
@@ -433,7 +511,7 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
         if (gi < P.n_items && dx * dx + dy * dy < reach * reach) imask |= 1u << gi;
         ixy[2 * gi] = it_x[i]; ixy[2 * gi + 1] = it_y[i];
       }
-      if (count_touch && k == 0) *itouch = 0ull;
+      if (count_touch && k == 0) { itouch[0] = 0ull; itouch[1] = 0ull; }
       imask |= __shfl_xor_sync(HRL_FULL_MASK, imask, 1);
       imask |= __shfl_xor_sync(HRL_FULL_MASK, imask, 2);
       __syncwarp();
@@ -467,11 +545,14 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
           if (fabsf(c.x - bx) > rr || fabsf(c.y - by) > rr) continue;
           nC = sphere_vs_aabb(c, crel, r, body + 4.f /* friction class of the cubes */, bx - hh, by - hh, P.item_z - hh, bx + hh, by + hh,
                               P.item_z + hh, P.margin, cands, lane, nC);
-          if (count_touch && (nC & 0x100)) atomicAdd(itouch, 1ull << (4 * gi));
+          if (count_touch && (nC & 0x100)) HRL_TOUCH_ADD(itouch, gi);
           nC &= 0xff;
         }
       }
     }
+    if (ITEMS && imask)  // cylinder part of the leg's capsules vs the cubes within reach: after the spheres, like the oracle
+      nC = min(nC + capsules_vs_cubes(s.O, K.rh, r_ank, r_tip, imask, ixy, P.item_half, P.item_z, P.margin, cands + lane, 32, nC, itouch, count_touch),
+               HRL_MAXC);
     // Maze box: the cylinder part of this leg's three capsules against the box's four vertical edges (the end-spheres
     // above only cover contacts at a capsule end; for a segment outside a convex rectangle the other closest pair is
     // (rectangle corner, segment interior); planar because the legs never reach the box's top).  Same order as the

@@ -31,7 +31,7 @@ struct WideMap {
   static constexpr int CL_FLOATS = EPW * HRL_CL_STRIDE;
   static constexpr int LAM_FLOATS = (CL_FLOATS + EPW * HRL_LAML_STRIDE + 3) / 4 * 4;
   static constexpr int CAND_FLOATS = HRL_MAXC * HRL_CAND_F * 4 * EPW;  // [c][field][env slot * 4 + leg]
-  static constexpr int ITEM_FLOATS = EPW * 32 + EPW * 2;
+  static constexpr int ITEM_FLOATS = EPW * 32 + EPW * 4;
   static constexpr int SMEM_FLOATS = ROWS_FLOATS + LAM_FLOATS + CAND_FLOATS + ITEM_FLOATS;
 };
 
@@ -173,7 +173,7 @@ __device__ __forceinline__ int leg_spheres_w(const AntLane& s, const SubstepPara
         if (fabsf(c.x - bx) > rr || fabsf(c.y - by) > rr) continue;
         n = sphere_vs_aabb_w<GS>(c, crel, r, body + 4.f, bx - hh, by - hh, P.item_z - hh, bx + hh, by + hh, P.item_z + hh, P.margin, cands, gl,
                                  base, n);
-        if (count_touch && (n & 0x100)) atomicAdd(itouch, 1ull << (4 * gi));
+        if (count_touch && (n & 0x100)) HRL_TOUCH_ADD(itouch, gi);
         n &= 0xff;
       }
     }
@@ -422,7 +422,7 @@ __device__ __forceinline__ void ant_substep_w(AntLane& s, const SubstepParams& P
     float* ixy = nullptr;
     unsigned long long* itouch = nullptr;
     if (ITEMS && P.item_contacts) {
-      ixy = iscr + es * 32; itouch = reinterpret_cast<unsigned long long*>(iscr + M::EPW * 32) + es;
+      ixy = iscr + es * 32; itouch = reinterpret_cast<unsigned long long*>(iscr + M::EPW * 32) + 2 * es;
       const float reach = 1.1314f + 1.4143f * (P.item_half + ant::R_CAPS + P.margin);
       if (sub * 4 + k == l) {  // (always true; keeps the compiler from hoisting the loads above the branch)
 #pragma unroll
@@ -433,7 +433,7 @@ __device__ __forceinline__ void ant_substep_w(AntLane& s, const SubstepParams& P
           ixy[2 * gi] = it_x[i]; ixy[2 * gi + 1] = it_y[i];
         }
       }
-      if (count_touch && l == 0) *itouch = 0ull;
+      if (count_touch && l == 0) { itouch[0] = 0ull; itouch[1] = 0ull; }
 #pragma unroll
       for (int o = 1; o < LPE; o <<= 1) imask |= __shfl_xor_sync(HRL_FULL_MASK, imask, o);
       __syncwarp();
@@ -458,6 +458,12 @@ __device__ __forceinline__ void ant_substep_w(AntLane& s, const SubstepParams& P
     if (__any_sync(HRL_FULL_MASK, n_mine > 0)) {
       int dummy = 0;
       leg_spheres_w<GS, ITEMS>(s, P, K.rh, r_ank, r_tip, k, si0, si1, incl - n_mine, cands, gl, imask, ixy, itouch, count_touch, dummy);
+    }
+    if (ITEMS) {  // capsule cylinders vs the cubes within reach: after the spheres, by sub-lane 0 of the leg
+      int ne = 0;
+      if (sub == 0 && imask)
+        ne = capsules_vs_cubes(s.O, K.rh, r_ank, r_tip, imask, ixy, P.item_half, P.item_z, P.margin, cands + gl, GS, total, itouch, count_touch);
+      total += __shfl_sync(HRL_FULL_MASK, ne, ebase | k);
     }
     if (!ITEMS && P.has_box) {  // capsule cylinders vs the box's vertical edges: after the spheres, by sub-lane 0 of the leg
       const float reach = 1.1314f + ant::R_CAPS + P.margin;

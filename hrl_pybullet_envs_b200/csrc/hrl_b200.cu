@@ -326,9 +326,9 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
     }
     if (FAMILY == 0 && P.item_contacts && mode == 0) {  // this lane's 4 cubes: contact points of the last sub-step
       __syncwarp();
-      const unsigned long long tw = reinterpret_cast<const unsigned long long*>(iscr + EPW * 32)[es];
+      const unsigned long long* tw = reinterpret_cast<const unsigned long long*>(iscr + EPW * 32) + 2 * es;
 #pragma unroll
-      for (int i = 0; i < IPL; i++) touch[i] = (int)((tw >> (4 * (IPL * l + i))) & 15ull);
+      for (int i = 0; i < IPL; i++) touch[i] = HRL_TOUCH_GET(tw, IPL * l + i);
       __syncwarp();
     }
     if (st.stats) {  // warp-uniform: inactive tail lanes contribute zeros (never guard a *_sync by `active`)

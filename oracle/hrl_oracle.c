@@ -289,7 +289,7 @@ struct hrlo_env {
   ant_model model;
   env_state* s;
   /* instrumentation: flop-model inputs */
-  double n_contacts, n_limit_rows, n_substeps;
+  double n_contacts, n_limit_rows, n_substeps, n_capsule_contacts; /* the last: contacts of a capsule's cylinder part */
   /* golden-vector replay (tests only): goal list instead of the Philox stream, stub robot */
   const double* replay_goals; /* [flag_max_targets][2], popped from the end like the reference */
   int replay_stub_robot;      /* next_target(): calc_potential() = -1, calc_state() leaves wtd alone */
@@ -511,6 +511,32 @@ static int sphere_vs_box(v3 c, real r, const float lo[3], const float hi[3], v3*
 
 /* `touched` (optional, [HRL_MAX_ITEMS]): contact points per food/poison cube, what
  * getContactPoints(robot) reports after the step (ant_gather_env.py:114) */
+/* The CYLINDER part of a capsule (segment A..B, radius r) against an axis-aligned box: the point of the segment's
+ * INTERIOR that is closest to the box.  The squared distance from A + t d to the box is convex in t with the continuous,
+ * monotone derivative g(t) = 2 sum_i e_i(t) d_i (e = the point's excess over the box, per axis); a minimum strictly
+ * inside (0, 1) exists iff g(0) < 0 < g(1) and is bracketed by 24 bisection steps.  (A minimum at an end is the end
+ * sphere's business.)  Normal and distance at that point are those of a sphere of radius r centred there. */
+static real seg_box_grad(v3 A, v3 d, const float lo[3], const float hi[3], real t) {
+  real g = 0;
+  for (int i = 0; i < 3; i++) {
+    real x = A.v[i] + t * d.v[i];
+    real e = x > (real)hi[i] ? x - (real)hi[i] : (x < (real)lo[i] ? x - (real)lo[i] : 0);
+    g += e * d.v[i];
+  }
+  return g;
+}
+static int capsule_interior_vs_box(v3 A, v3 B, real r, const float lo[3], const float hi[3], v3* Q, v3* n, real* dist) {
+  v3 d = vsub(B, A);
+  if (!(seg_box_grad(A, d, lo, hi, 0) < 0 && seg_box_grad(A, d, lo, hi, 1) > 0)) return 0;
+  real a = 0, b = 1;
+  for (int it = 0; it < 24; it++) {
+    real m = (a + b) / 2;
+    if (seg_box_grad(A, d, lo, hi, m) < 0) a = m; else b = m;
+  }
+  *Q = vadd(A, vscale(d, (a + b) / 2));
+  return sphere_vs_box(*Q, r, lo, hi, n, dist);
+}
+
 static int detect_contacts(const hrlo_env* E, const env_state* s, const kin_t* K, contact_t* C, int feet_ground[4],
                            int* touched) {
   const hrl_config* cfg = &E->cfg;
@@ -592,6 +618,36 @@ static int detect_contacts(const hrlo_env* E, const env_state* s, const kin_t* K
           v3 nrm = V3(ex / el, ey / el, 0);
           C[n].sphere = -1; C[n].link = link; C[n].n = nrm; C[n].dist = dist; C[n].P = vsub(Q, vscale(nrm, rc));
           C[n].mu = (real)cfg->friction; C[n].item = -1;
+          n++;
+        }
+      }
+    }
+    /* Food / poison cubes: the cylinder part of the leg's three capsules (assets/ant.xml:16-24 capsules vs the 0.25 m
+     * boxes of assets/food.xml:17-22) - a leg lying across a cube's edge touches it between its end spheres.  After the
+     * last sphere of leg k; cubes in index order, capsules foot, aux, leg.  Each such contact is a contact POINT of the
+     * robot with the cube (ant_gather_env.py:113-116 counts them). */
+    if (cfg->item_contacts && si >= 1 && (si - 1) % 3 == 2) {
+      int k = (si - 1) / 3;
+      real sx = (real)LEG_SX[k], sy = (real)LEG_SY[k], rc = (real)ANT_R_CAPS, hh = (real)cfg->item_half, rr = hh + rc + margin;
+      for (int i = 0; i < cfg->n_food + cfg->n_poison; i++) {
+        real bx = s->items[i][0], by = s->items[i][1];
+        float lo[3] = {(float)bx - cfg->item_half, (float)by - cfg->item_half, cfg->item_z - cfg->item_half};
+        float hi[3] = {(float)bx + cfg->item_half, (float)by + cfg->item_half, cfg->item_z + cfg->item_half};
+        for (int cap = 0; cap < 3; cap++) {
+          int link = 3 + 3 * k - cap;  /* foot, aux, leg */
+          real len = (cap == 0) ? (real)0.4 : (real)0.2;
+          v3 A = K->ow[link], B = vadd(A, mmulv(&K->Rw[link], V3(len * sx, len * sy, 0)));
+          real x0 = A.v[0] < B.v[0] ? A.v[0] : B.v[0], x1 = A.v[0] < B.v[0] ? B.v[0] : A.v[0];
+          real y0 = A.v[1] < B.v[1] ? A.v[1] : B.v[1], y1 = A.v[1] < B.v[1] ? B.v[1] : A.v[1];
+          if (bx < x0 - rr || bx > x1 + rr || by < y0 - rr || by > y1 + rr) continue;
+          v3 Q, nrm; real dist;
+          if (!capsule_interior_vs_box(A, B, rc, lo, hi, &Q, &nrm, &dist)) continue;
+          if (!(dist < margin)) continue;
+          if (touched) touched[i]++;
+          if (per_group[k] >= MAX_CONTACT_PER_GROUP) continue;
+          per_group[k]++;
+          C[n].sphere = -1; C[n].link = link; C[n].n = nrm; C[n].dist = dist; C[n].P = vsub(Q, vscale(nrm, rc));
+          C[n].mu = (real)cfg->item_friction; C[n].item = i;
           n++;
         }
       }
@@ -713,6 +769,7 @@ static int ant_substep(hrlo_env* E, env_state* s, const real tau[8], int feet_gr
     row_finish(E, &K, &fr[2 * c + 1], u, 0, 0, h, 0);
   }
   E->n_contacts += nc; E->n_limit_rows += nl; E->n_substeps += 1;
+  for (int c = 0; c < nc; c++) if (C[c].sphere < 0) E->n_capsule_contacts += 1;
 
   real dv[NDOF];
   for (int i = 0; i < NDOF; i++) dv[i] = 0;
@@ -1773,6 +1830,15 @@ int hrlo_free_accel(hrlo_env* E, int e, const real* tau, real* udot) {
   kin_t K;
   forward_kinematics(&E->model, &E->s[e], &K);
   return aba(E, &E->s[e], &K, tau, udot);
+}
+double hrlo_capsule_contacts(hrlo_env* E) { return E->n_capsule_contacts; }
+/* test hook: closest interior point of the segment A..B to the box (capsule_interior_vs_box); out = Q(3), n(3), dist */
+int hrlo_capsule_vs_box(const double A[3], const double B[3], double r, const float lo[3], const float hi[3], double out[7]) {
+  v3 Q, n; real dist;
+  if (!capsule_interior_vs_box(V3((real)A[0], (real)A[1], (real)A[2]), V3((real)B[0], (real)B[1], (real)B[2]), (real)r, lo, hi, &Q, &n, &dist)) return 0;
+  for (int i = 0; i < 3; i++) { out[i] = (double)Q.v[i]; out[3 + i] = (double)n.v[i]; }
+  out[6] = (double)dist;
+  return 1;
 }
 void hrlo_stats(hrlo_env* E, double out[3]) { out[0] = E->n_contacts; out[1] = E->n_limit_rows; out[2] = E->n_substeps; }
 void hrlo_rng_u4(uint64_t seed, uint32_t env, uint32_t stream, uint32_t draw, uint32_t sub, double* u) {

@@ -681,9 +681,13 @@ def test_cube_colliders_and_contact_pickup(kw):
         events += int((np.abs(info["food_rew"].cpu().numpy()) > 0).sum())
         contacts = o.stats()["contacts_per_substep"]
     assert n_out <= 0.02 * checked, (n_out, checked)   # more knife-edge contacts than on flat ground: box edges
+    import ctypes
+    o.L.hrlo_capsule_contacts.restype = ctypes.c_double; o.L.hrlo_capsule_contacts.argtypes = [ctypes.c_void_p]
+    n_cyl = o.L.hrlo_capsule_contacts(o.h)
+    assert n_cyl > 20, n_cyl                           # legs lying across cube edges: contacts of the capsules' cylinder part too
     if not (kw.get("robot_coll_dist", 1) > 0):
         assert events > 20, events                     # the feet do touch cubes in this set-up
-    print("cube test", kw, "pickup events", events, "contacts/substep", contacts, "outliers", n_out, "/", checked)
+    print("cube test", kw, "pickup events", events, "contacts/substep", contacts, "cylinder contacts", n_cyl, "outliers", n_out, "/", checked)
 
 
 def test_episode_statistics_match_rewards():

@@ -189,3 +189,36 @@ def test_capsule_cylinder_meets_the_maze_box_corner():
     assert np.abs(p0[:2]).max() < 1e-3   # (link-constant tabulation differences of 4e-6 x a 25 rad/s limit correction)
     n = np.array([1.0, -1.0]) / np.sqrt(2.0)
     assert p1[:2] @ n > 0.1   # (the tangential part is friction: the foot swings under the limit correction)
+
+
+def test_capsule_cylinder_vs_box_closest_point():
+    """capsule_interior_vs_box (the cylinder part of a leg capsule against a food / poison cube): the bisection on the
+    derivative of the squared point-box distance finds the segment's interior point closest to the box - checked against
+    a brute-force scan - and reports nothing when the closest point is an END of the segment (the end spheres' job)."""
+    import ctypes as C
+    L = O.lib()
+    L.hrlo_capsule_vs_box.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(5)
+    lo = np.array([-0.125, -0.125, -0.025], np.float32); hi = np.array([0.125, 0.125, 0.225], np.float32)
+    found = ends = 0
+    for _ in range(400):
+        A = rng.uniform(-0.6, 0.6, 3); B = A + rng.normal(size=3) * 0.4
+        A[2] = abs(A[2]); B[2] = abs(B[2])
+        out = np.zeros(7)
+        ok = L.hrlo_capsule_vs_box(O._p(A), O._p(B), 0.08, O._p(lo), O._p(hi), O._p(out))
+        t = np.linspace(0, 1, 20001)[:, None]
+        P = A + t * (B - A)
+        e = np.maximum(P - hi, 0) + np.minimum(P - lo, 0)
+        d = np.linalg.norm(e, axis=1)
+        j = int(d.argmin())
+        interior = 0 < j < 20000 and d[j] > 0
+        if ok:
+            found += 1
+            if d.min() > 0:
+                assert abs(out[6] - (d.min() - 0.08)) < 1e-5, (out[6], d.min())
+                np.testing.assert_allclose(out[:3], P[j], atol=2e-4)
+                np.testing.assert_allclose(out[3:6], e[j] / d[j], atol=2e-3)
+        else:
+            ends += 1
+            assert not interior or d[j] < 1e-9 or min(j, 20000 - j) < 3, (j, d[j])   # minimum at an end (or the segment starts inside)
+    assert found > 50 and ends > 50
