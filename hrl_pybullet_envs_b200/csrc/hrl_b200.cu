@@ -212,16 +212,75 @@ template <int SUB>
 constexpr bool tiles_fit() { return Map<SUB>::ROWS_FLOATS >= Map<SUB>::EPW * HRL_OBS_STAGE + 2 * Map<SUB>::EPW * 2 * HRL_MAX_BINS; }
 static_assert(tiles_fit<1>() && tiles_fit<2>() && tiles_fit<4>(), "task-layer tiles must fit in the row buffer");
 
+// ------------------------------------------------------------------------------------------
+// fused rollout ("policy-inference fusion"): T steps in ONE launch, the actions of every step
+// computed in-kernel by a small MLP policy from the observation the previous step left in shared memory
+//   a = tanh(W3 tanh(W2 tanh(W1 obs + b1) + b2) + b3) + sigma * N(0, 1)
+// weights packed input-major: W1[D][H] b1[H] W2[H][H] b2[H] W3[H][8] b3[8], H = 32 or 64.
+// The 4 lanes of an env split the hidden units (H / 4 each); lane k ends up with the two actions of ITS leg.
+// ------------------------------------------------------------------------------------------
+struct RollArgs {
+  int T, H;
+  const float* w;
+  float sigma;
+  unsigned long long seed;
+  float* act_out;  // [T][N][8]
+};
+enum { STREAM_POLICY = 6 };
+
+template <int HQ>
+__device__ __forceinline__ void mlp_layer(const float* __restrict__ w, const float* __restrict__ b, int n_in, const float* __restrict__ x,
+                                          int k, float* __restrict__ out) {
+  constexpr int H = 4 * HQ;
+  float acc[HQ];
+#pragma unroll
+  for (int u = 0; u < HQ; u += 4) {
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(b + k * HQ + u));
+    acc[u] = bv.x; acc[u + 1] = bv.y; acc[u + 2] = bv.z; acc[u + 3] = bv.w;
+  }
+#pragma unroll 2
+  for (int j = 0; j < n_in; j++) {
+    const float xj = x[j];
+#pragma unroll
+    for (int u = 0; u < HQ; u += 4) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + j * H + k * HQ + u));
+      acc[u] = fmaf(xj, wv.x, acc[u]); acc[u + 1] = fmaf(xj, wv.y, acc[u + 1]);
+      acc[u + 2] = fmaf(xj, wv.z, acc[u + 2]); acc[u + 3] = fmaf(xj, wv.w, acc[u + 3]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < HQ; u++) out[k * HQ + u] = tanhf(acc[u]);
+}
+// obs: this env's staged observation (shared memory), scratch: 2 x 64 floats of this env (shared memory)
+template <int HQ>
+__device__ __forceinline__ float2 mlp_policy(const RollArgs& ra, int D, const float* __restrict__ obs, float* __restrict__ scratch, int k) {
+  constexpr int H = 4 * HQ;
+  const float* w1 = ra.w, *b1 = w1 + D * H, *w2 = b1 + H, *b2 = w2 + H * H, *w3 = b2 + H, *b3 = w3 + H * 8;
+  mlp_layer<HQ>(w1, b1, D, obs, k, scratch);
+  __syncwarp();
+  mlp_layer<HQ>(w2, b2, H, scratch, k, scratch + 64);
+  __syncwarp();
+  float2 o = __ldg(reinterpret_cast<const float2*>(b3 + 2 * k));
+#pragma unroll 4
+  for (int j = 0; j < H; j++) {
+    const float xj = scratch[64 + j];
+    const float2 wv = __ldg(reinterpret_cast<const float2*>(w3 + j * 8 + 2 * k));
+    o.x = fmaf(xj, wv.x, o.x); o.y = fmaf(xj, wv.y, o.y);
+  }
+  __syncwarp();
+  return make_float2(tanhf(o.x), tanhf(o.y));
+}
+
 #ifdef HRL_DEBUG_CONTACTS
 __device__ float* g_dbg_contacts = nullptr;  // [N][4 legs][40]: candidate lists of the first sub-step of the last launch
 #endif
 
-template <int FAMILY, int SUB>
+template <int FAMILY, int SUB, int ROLL = 0>
 __global__ void __launch_bounds__(32 * HRL_WARPS_PER_CTA, Map<SUB>::MIN_CTAS)
-ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float* __restrict__ bounds, int n_lines,
-               const float* __restrict__ actions, const uint8_t* __restrict__ mask, float* __restrict__ obs_out,
-               float* __restrict__ rew_out, uint8_t* __restrict__ done_out, float* __restrict__ info_out,
-               float* __restrict__ term_out, int mode, int n_sub, int D) {
+ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float* __restrict__ bounds_g, int n_lines,
+               const float* __restrict__ actions, const uint8_t* __restrict__ mask, float* __restrict__ obs_out_g,
+               float* __restrict__ rew_out_g, uint8_t* __restrict__ done_out_g, float* __restrict__ info_out,
+               float* __restrict__ term_out, int mode_g, int n_sub, int D, RollArgs ra = RollArgs()) {
   extern __shared__ __align__(16) float smem[];
   typedef Map<SUB> M;
   constexpr int LPE = M::LPE, EPW = M::EPW, IPL = M::IPL;
@@ -279,6 +338,15 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
     }
   }
 
+  // ROLL: step -1 composes the initial observation (what hrl_observe does), steps 0 .. T-1 are full env steps whose
+  // actions come from the in-kernel policy; the robot / task state stays in registers in between.  Otherwise ONE pass.
+#pragma unroll 1
+  for (int step = ROLL ? -1 : 0; step < (ROLL ? ra.T : 1); step++) {
+  const int mode = ROLL ? (step < 0 ? 3 : 0) : mode_g;
+  float* __restrict__ obs_out = ROLL ? obs_out_g + (size_t)(step + 1) * N * D : obs_out_g;
+  float* __restrict__ rew_out = ROLL ? rew_out_g + (size_t)max(step, 0) * N : rew_out_g;
+  uint8_t* __restrict__ done_out = ROLL ? done_out_g + (size_t)max(step, 0) * N : done_out_g;
+  const float* __restrict__ bounds = bounds_g;
   // ---- physics ----
   float act1 = 0.f, act2 = 0.f;
   int feet_ground = 0;
@@ -293,7 +361,22 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
     for (int i = lane; i < M::LAM_FLOATS / 4; i += 32)
       reinterpret_cast<float4*>(rows + M::ROWS_FLOATS)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
-    const float2 a = reinterpret_cast<const float2*>(actions)[e * 4 + k];
+    float2 a;
+    if (ROLL) {  // the policy reads the observation the previous pass staged in shared memory (sobs is dense: [EPW][D])
+      float* scr = cands + es * 128;
+      a = ra.H == 64 ? mlp_policy<16>(ra, D, sobs + es * D, scr, k) : mlp_policy<8>(ra, D, sobs + es * D, scr, k);
+      if (ra.sigma > 0.f) {  // exploration noise: Box-Muller on the counter RNG, keyed by (seed, env), addressed by the env's step count
+        float u[4];
+        rng_u4(ra.seed, genv, STREAM_POLICY, (uint32_t)T.steps_total, (uint32_t)k, u);
+        const float r0 = sqrtf(-2.f * logf(u[0] + 2.98e-8f));
+        float sn, cs;
+        sincosf(6.2831853f * u[1], &sn, &cs);
+        a.x += ra.sigma * r0 * cs; a.y += ra.sigma * r0 * sn;
+      }
+      if (active && sub == 0) reinterpret_cast<float2*>(ra.act_out)[((size_t)step * N + e) * 4 + k] = a;
+    } else {
+      a = reinterpret_cast<const float2*>(actions)[e * 4 + k];
+    }
     act1 = a.x; act2 = a.y;
     // WalkerBase.apply_action [3P-MEM]: clip to +-1, torque = power * power_coef * a
     const float tau1 = cfg.torque_scale * fminf(fmaxf(act1, -1.f), 1.f);
@@ -705,6 +788,28 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
     todo = next_todo;
   }
 
+  if (mode != 1 && obs_out) {
+    __syncwarp();
+    // coalesced write-back of the staged observation rows (8 consecutive envs = one contiguous span)
+    unsigned wmask = 0xffffffffu;
+    if (mode == 2) {
+      const bool m = mask ? (mask[e] != 0) : true;
+      wmask = __ballot_sync(HRL_FULL_MASK, m);
+    }
+    float* dst = obs_out + (size_t)env0 * D;
+    if (env0 + EPW <= N && wmask == 0xffffffffu && ((EPW * D) & 3) == 0 && (((uintptr_t)dst & 15) == 0)) {
+      // common case: one contiguous, 16-byte aligned span -> float4 stores, no index arithmetic
+      for (int i = lane; i < EPW * D / 4; i += 32) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(sobs)[i];
+    } else {
+      for (int i = lane; i < EPW * D; i += 32) {
+        const int w8 = i / D;
+        if (env0 + w8 < N && ((wmask >> (LPE * w8)) & 1u)) dst[i] = sobs[i];
+      }
+    }
+    if (ROLL) __syncwarp();
+  }
+  }  // step loop
+
   // ---- store ----
   if (active) {
     if (l == 0) {
@@ -726,25 +831,6 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
         st.items[e * 8 + l] = make_float4(it_x[0], it_y[0], it_x[IPL - 1], it_y[IPL - 1]);
       } else {
         reinterpret_cast<float2*>(st.items)[e * 16 + l] = make_float2(it_x[0], it_y[0]);
-      }
-    }
-  }
-  if (mode != 1 && obs_out) {
-    __syncwarp();
-    // coalesced write-back of the staged observation rows (8 consecutive envs = one contiguous span)
-    unsigned wmask = 0xffffffffu;
-    if (mode == 2) {
-      const bool m = mask ? (mask[e] != 0) : true;
-      wmask = __ballot_sync(HRL_FULL_MASK, m);
-    }
-    float* dst = obs_out + (size_t)env0 * D;
-    if (env0 + EPW <= N && wmask == 0xffffffffu && ((EPW * D) & 3) == 0 && (((uintptr_t)dst & 15) == 0)) {
-      // common case: one contiguous, 16-byte aligned span -> float4 stores, no index arithmetic
-      for (int i = lane; i < EPW * D / 4; i += 32) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(sobs)[i];
-    } else {
-      for (int i = lane; i < EPW * D; i += 32) {
-        const int w8 = i / D;
-        if (env0 + w8 < N && ((wmask >> (LPE * w8)) & 1u)) dst[i] = sobs[i];
       }
     }
   }
@@ -1285,6 +1371,9 @@ int hrl_create(const hrl_config* cfg, int32_t device, hrl_handle** out) {
   CKH(cudaFuncSetAttribute(ant_env_kernel<FAM, SUB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
   OPT_IN(0, 1); OPT_IN(1, 1); OPT_IN(0, 2); OPT_IN(1, 2); OPT_IN(0, 4); OPT_IN(1, 4);
 #undef OPT_IN
+  // the fused-rollout instantiations read their policy weights through L1: leave it room (no max-shared carve-out)
+  CKH(cudaFuncSetAttribute(ant_env_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HRL_WARPS_PER_CTA * Map<1>::SMEM_FLOATS * (int)sizeof(float)));
+  CKH(cudaFuncSetAttribute(ant_env_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HRL_WARPS_PER_CTA * Map<1>::SMEM_FLOATS * (int)sizeof(float)));
   h->sub = default_sub();
   // like the reference, reset() must be called before the first step(); an un-reset env has a
   // zero quaternion, produces a non-finite observation and is ended by the NaN guard
@@ -1455,6 +1544,30 @@ int hrl_flagrun_next_target(hrl_handle* h, const uint8_t* d_mask, void* stream) 
   if (h->cfg.env_kind != HRL_ANT_FLAGRUN) return set_err(HRL_E_INVALID, "hrl_flagrun_next_target: not an AntFlagrun handle");
   ON_DEVICE(h->device);
   flag_next_kernel<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->cfg, h->st, d_mask);
+  g_launches++;
+  CK(cudaGetLastError());
+  return HRL_OK;
+}
+
+/* Fused rollout: T env steps in ONE launch with an in-kernel MLP policy (see mlp_policy). */
+int hrl_rollout_mlp(hrl_handle* h, int32_t T, const float* d_weights, int32_t hidden, float sigma, uint64_t noise_seed, float* d_obs,
+                    float* d_act, float* d_rew, uint8_t* d_done, void* stream) {
+  if (!h || T < 1 || !d_weights || !d_obs || !d_act || !d_rew || !d_done) return set_err(HRL_E_INVALID, "bad argument to hrl_rollout_mlp");
+  if (hidden != 32 && hidden != 64) return set_err(HRL_E_INVALID, "hrl_rollout_mlp: hidden width must be 32 or 64");
+  if (h->cfg.env_kind == HRL_POINT_GATHER) return set_err(HRL_E_INVALID, "hrl_rollout_mlp: Ant envs only");
+  if (!(sigma >= 0.f)) return set_err(HRL_E_INVALID, "hrl_rollout_mlp: sigma must be >= 0");
+  ON_DEVICE(h->device);
+  DevState st = h->st;
+  st.fin_flag = nullptr;
+  RollArgs ra;
+  ra.T = T; ra.H = hidden; ra.w = d_weights; ra.sigma = sigma; ra.seed = noise_seed; ra.act_out = d_act;
+  const int Tn = 32 * HRL_WARPS_PER_CTA, EPC = Map<1>::EPW * HRL_WARPS_PER_CTA, G = (h->N + EPC - 1) / EPC;
+  const size_t smem = (size_t)HRL_WARPS_PER_CTA * Map<1>::SMEM_FLOATS * sizeof(float);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->cfg.env_kind == HRL_ANT_GATHER)
+    ant_env_kernel<0, 1, 1><<<G, Tn, smem, s>>>(h->cfg, st, h->d_bounds, h->n_lines, nullptr, nullptr, d_obs, d_rew, d_done, nullptr, nullptr, 0, 0, h->D, ra);
+  else
+    ant_env_kernel<1, 1, 1><<<G, Tn, smem, s>>>(h->cfg, st, h->d_bounds, h->n_lines, nullptr, nullptr, d_obs, d_rew, d_done, nullptr, nullptr, 0, 0, h->D, ra);
   g_launches++;
   CK(cudaGetLastError());
   return HRL_OK;

@@ -250,6 +250,38 @@ class VecEnv:
                 self.step(a[t], out=buf.slot(t))
         return g, buf
 
+    @staticmethod
+    def pack_mlp(layers):
+        """Pack ((W1, b1), (W2, b2), (W3, b3)) in torch.nn.Linear layout (W[out, in]) into the input-major float32 vector
+        `hrl_rollout_mlp` reads: W1^T b1 W2^T b2 W3^T b3."""
+        parts = []
+        for W, b in layers:
+            parts += [W.detach().to(torch.float32).t().contiguous().reshape(-1), b.detach().to(torch.float32).reshape(-1)]
+        return torch.cat(parts).contiguous()
+
+    def rollout_mlp(self, layers, horizon, buf=None, sigma=0.0, noise_seed=0):
+        """Fused rollout (include/hrl_b200.h `hrl_rollout_mlp`): `horizon` steps in ONE kernel launch, actions from the
+        3-layer tanh MLP `layers` = ((W1[H, D], b1), (W2[H, H], b2), (W3[8, H], b3)) evaluated inside the kernel (H = 32 or
+        64), plus N(0, sigma^2) exploration noise.  Fills and returns a RolloutBuffer: obs[0..T], act, rew, done."""
+        if self.kind == HRL_POINT_GATHER:
+            raise TypeError("rollout_mlp: Ant envs only")
+        (W1, b1), (W2, b2), (W3, b3) = layers
+        H = W1.shape[0]
+        if H not in (32, 64) or tuple(W1.shape) != (H, self.D) or tuple(W2.shape) != (H, H) or tuple(W3.shape) != (self.A, H):
+            raise ValueError("layers must be ((W1[H,%d], b1[H]), (W2[H,H], b2[H]), (W3[%d,H], b3[%d])) with H = 32 or 64" % (self.D, self.A, self.A))
+        w = self.pack_mlp(layers).to(self.device)
+        buf = buf or RolloutBuffer(self, horizon)
+        if buf.T < horizon:
+            raise ValueError("rollout buffer holds %d steps, need %d" % (buf.T, horizon))
+        if _NVTX:
+            torch.cuda.nvtx.range_push("hrl.rollout_mlp")
+        _cabi.check(self.L.hrl_rollout_mlp(self.h, int(horizon), _ptr(w), int(H), float(sigma), int(noise_seed), _ptr(buf.obs), _ptr(buf.act),
+                                           _ptr(buf.rew), _ptr(buf.done), self._stream()))
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        self._keep = w   # the launch is asynchronous: keep the packed weights alive
+        return buf
+
     def rollout_buffer(self, horizon):
         """Device-resident storage for ``horizon`` steps; ``step(a, out=buf.slot(t))`` fills slot t in place."""
         return RolloutBuffer(self, horizon)

@@ -199,6 +199,18 @@ int hrl_set_host_mode(hrl_handle* h, int32_t mode);
  * (obs f32[N,D] | rew f32[N] | info f32[N,4] | done u8[N], 256-byte aligned sections); total bytes. */
 int hrl_host_layout(const hrl_config* cfg, size_t* off_rew, size_t* off_info, size_t* off_done, size_t* total);
 
+/* Fused rollout with an in-kernel policy ("policy-inference fusion"; no counterpart in the reference,
+ * whose users call step() once per action: README.md:20-37).  ONE launch runs T consecutive env steps of all N Ant envs;
+ * the action of every step is computed in the kernel from the observation the previous step produced, by the MLP
+ *     a = tanh(W3 tanh(W2 tanh(W1 obs + b1) + b2) + b3) + sigma * N(0, 1)           (then clipped like any action)
+ * so neither observations nor actions leave the SM between steps and the robot state stays in registers.
+ *   d_weights f32, packed INPUT-major: W1[obs_dim][H] b1[H] W2[H][H] b2[H] W3[H][8] b3[8], H = hidden = 32 or 64
+ *   d_obs f32[T+1, N, obs_dim] (slot 0 = the observation before the first step), d_act f32[T, N, 8] (the actions taken,
+ *   before clipping), d_rew f32[T, N], d_done u8[T, N].  Auto-reset as in hrl_step; info / terminal observations are not
+ *   produced.  noise_seed keys the counter RNG of the exploration noise (addressed by env and step count). */
+int hrl_rollout_mlp(hrl_handle* h, int32_t T, const float* d_weights, int32_t hidden, float sigma, uint64_t noise_seed,
+                    float* d_obs, float* d_act, float* d_rew, uint8_t* d_done, void* stream);
+
 /* Replaces saveState/restoreState (used as the reset mechanism by pybullet_envs) and gives
  * the "identical saved states" hook the one-step parity tests need.
  *   d_fstate f32[N, HRL_STATE_F], d_istate i32[N, HRL_STATE_I]. */

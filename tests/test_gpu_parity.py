@@ -809,3 +809,62 @@ def test_cuda_graph_rollout_matches_stepping():
     for t in range(T):
         o, r, d, _ = a.step(acts[t])
         assert torch.equal(o, buf.obs[t + 1]) and torch.equal(r, buf.rew[t]) and torch.equal(d, buf.done[t])
+
+
+# ------------------------------------------------------------------ fused rollout with an in-kernel MLP policy
+def _mlp(D, H, A=8, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    def lin(o, i, s):
+        return ((torch.rand(o, i, generator=g) * 2 - 1) * s).cuda(), ((torch.rand(o, generator=g) * 2 - 1) * 0.1).cuda()
+    return (lin(H, D, 0.3), lin(H, H, 0.2), lin(A, H, 0.3))
+
+
+def _mlp_forward(layers, obs):
+    x = obs
+    for W, b in layers:
+        x = torch.tanh(x @ W.t() + b)
+    return x
+
+
+@pytest.mark.parametrize("env_id,H", [("AntGatherBulletEnv-v0", 64), ("AntMazeBulletEnv-v0", 32), ("AntFlagrunBulletEnv-v0", 64)])
+def test_fused_rollout_matches_policy_plus_stepping(env_id, H):
+    """hrl_rollout_mlp: (1) the in-kernel MLP equals the torch MLP on the observation it saw (1e-5), at every step;
+    (2) replaying the actions it recorded through plain step() calls from the same initial state reproduces its
+    observations / rewards / dones exactly - the fused loop is the same env, including auto-resets (episodes of 5 steps)."""
+    from hrl_pybullet_envs_b200 import VecEnv
+    N, T = 200, 12    # 200: a ragged last warp
+    a = VecEnv(env_id, N, seed=13, max_episode_steps=5); b = VecEnv(env_id, N, seed=13, max_episode_steps=5)
+    layers = _mlp(a.D, H)
+    oa = a.reset().clone(); b.reset()
+    for t in range(3):   # leave the reset pose behind
+        act = (torch.rand(N, 8, device="cuda") * 2 - 1)
+        a.step(act); b.step(act)
+    buf = a.rollout_mlp(layers, T)
+    torch.cuda.synchronize()
+    assert torch.isfinite(buf.obs).all() and buf.done.any() and not buf.done.all()
+    for t in range(T):
+        want = _mlp_forward(layers, buf.obs[t])
+        assert (buf.act[t] - want).abs().max() < 1e-5, (t, float((buf.act[t] - want).abs().max()))
+    ob = b.observe()
+    assert torch.equal(ob, buf.obs[0])
+    for t in range(T):
+        o, r, d, _ = b.step(buf.act[t])
+        assert torch.equal(o, buf.obs[t + 1]) and torch.equal(r, buf.rew[t]) and torch.equal(d, buf.done[t]), t
+    fa, ia = a.get_state(); fb, ib = b.get_state()
+    assert torch.equal(fa, fb) and torch.equal(ia, ib)
+
+
+def test_fused_rollout_exploration_noise():
+    from hrl_pybullet_envs_b200 import VecEnv
+    N = 4096
+    layers = _mlp(46, 64, seed=1)
+    acts = {}
+    for tag, sigma, seed in (("det", 0.0, 0), ("s1", 0.5, 1), ("s1b", 0.5, 1), ("s2", 0.5, 2)):
+        e = VecEnv("AntGatherBulletEnv-v0", N, seed=3)
+        e.reset()
+        acts[tag] = e.rollout_mlp(layers, 1, sigma=sigma, noise_seed=seed).act[0].clone()
+    eps = (acts["s1"] - acts["det"]) / 0.5
+    assert abs(float(eps.mean())) < 0.02 and abs(float(eps.std()) - 1.0) < 0.02          # N(0, 1) per action component
+    assert torch.equal(acts["s1"], acts["s1b"]) and not torch.equal(acts["s1"], acts["s2"])
+    c = torch.corrcoef(eps.t())                                                            # the 8 components are independent
+    assert (c - torch.eye(8, device="cuda")).abs().max() < 0.06
