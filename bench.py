@@ -323,6 +323,43 @@ def run_ours(args):
         graph_ms = e0.elapsed_time(e1) / (reps * T)
         del graph, buf
 
+    # ---- timed region 2c (consumer side, informational): T = 32 steps WITH a policy - the fused rollout (in-kernel
+    # 46-64-64-8 tanh MLP, one launch per 32 steps) against the same MLP in torch followed by step(), per step
+    policy = None
+    if A == 8 and not args.no_graph:
+        gp = torch.Generator(device=dev).manual_seed(7)
+        def lin(o, i, sc):
+            return ((torch.rand(o, i, generator=gp, device=dev) * 2 - 1) * sc, (torch.rand(o, generator=gp, device=dev) * 2 - 1) * 0.1)
+        layers = (lin(64, D, 0.3), lin(64, 64, 0.2), lin(8, 64, 0.3))
+        T = 32
+        rbuf = env.rollout_buffer(T)
+        env.rollout_mlp(layers, T, buf=rbuf); torch.cuda.synchronize()
+        reps = max(min(K, 640) // T, 2)
+        barrier()
+        e0.record()
+        for _ in range(reps):
+            env.rollout_mlp(layers, T, buf=rbuf, sigma=0.1, noise_seed=1)
+        e1.record()
+        barrier()
+        fused_us = e0.elapsed_time(e1) * 1e3 / (reps * T)
+        obs_t = env.observe()
+        for _ in range(3):                       # cuBLAS handle / kernel-module loading happens here, not in the timed loop
+            x = obs_t
+            for W, b in layers:
+                x = torch.tanh(torch.addmm(b, x, W.t()))
+        barrier()
+        e0.record()
+        for _ in range(reps * T):
+            x = obs_t
+            for W, b in layers:
+                x = torch.tanh(torch.addmm(b, x, W.t()))
+            obs_t, _, _, _ = env.step(x)
+        e1.record()
+        barrier()
+        policy = {"fused_rollout_us_per_step": fused_us, "torch_mlp_plus_step_us_per_step": e0.elapsed_time(e1) * 1e3 / (reps * T),
+                  "policy": "%d-64-64-8 tanh MLP, sigma 0.1" % D, "steps_per_launch": T,
+                  "env_steps_per_s_fused": N * world / (fused_us * 1e-6)}
+
     # ---- timed region 3 (e2e): the public API with HOST buffers, per step: actions in pinned host memory -> device,
     # kernel, obs/rew/done/info -> pinned host memory, completion visible to the host.  Both transfer modes of
     # hrl_step_host; the default ("auto" = zero-copy for pinned buffers) is the headline.  Median of 5 segments of K steps.
@@ -387,6 +424,7 @@ def run_ours(args):
                        "ms_per_step_back_to_back": b2b_ms_max / K,
                        "value_back_to_back": total_envs * K / (b2b_ms_max * 1e-3),
                        "ms_per_step_cuda_graph": graph_ms_max if graph_ms is not None else None,
+                       "policy_rollout": policy,
                        "parity": "task layer pinned on reference-executed fixtures; physics vs our own f64 oracle port only "
                                  "(pybullet absent: parity unpinned against real Bullet)"},
             "e2e": {"value": total_envs * K / (e2e_ms * 1e-3), "unit": UNIT,

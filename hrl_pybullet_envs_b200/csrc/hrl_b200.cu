@@ -228,55 +228,61 @@ struct RollArgs {
 };
 enum { STREAM_POLICY = 6 };
 
+// The weights live in shared memory (staged once per launch, shared by the warps of the CTA).  Lane k owns the float4
+// groups g = 4 q + k of a layer's H / 4 groups: for a fixed q the 4 lanes of an env read 64 contiguous bytes (no bank
+// conflict; the 8 envs of the warp read the same addresses: broadcast).
 template <int HQ>
 __device__ __forceinline__ void mlp_layer(const float* __restrict__ w, const float* __restrict__ b, int n_in, const float* __restrict__ x,
                                           int k, float* __restrict__ out) {
   constexpr int H = 4 * HQ;
   float acc[HQ];
 #pragma unroll
-  for (int u = 0; u < HQ; u += 4) {
-    const float4 bv = __ldg(reinterpret_cast<const float4*>(b + k * HQ + u));
-    acc[u] = bv.x; acc[u + 1] = bv.y; acc[u + 2] = bv.z; acc[u + 3] = bv.w;
+  for (int q = 0; q < HQ / 4; q++) {
+    const float4 bv = *reinterpret_cast<const float4*>(b + (4 * q + k) * 4);
+    acc[4 * q] = bv.x; acc[4 * q + 1] = bv.y; acc[4 * q + 2] = bv.z; acc[4 * q + 3] = bv.w;
   }
-#pragma unroll 2
+#pragma unroll 4
   for (int j = 0; j < n_in; j++) {
     const float xj = x[j];
 #pragma unroll
-    for (int u = 0; u < HQ; u += 4) {
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + j * H + k * HQ + u));
-      acc[u] = fmaf(xj, wv.x, acc[u]); acc[u + 1] = fmaf(xj, wv.y, acc[u + 1]);
-      acc[u + 2] = fmaf(xj, wv.z, acc[u + 2]); acc[u + 3] = fmaf(xj, wv.w, acc[u + 3]);
+    for (int q = 0; q < HQ / 4; q++) {
+      const float4 wv = *reinterpret_cast<const float4*>(w + j * H + (4 * q + k) * 4);
+      acc[4 * q] = fmaf(xj, wv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(xj, wv.y, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(xj, wv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(xj, wv.w, acc[4 * q + 3]);
     }
   }
 #pragma unroll
-  for (int u = 0; u < HQ; u++) out[k * HQ + u] = tanhf(acc[u]);
+  for (int q = 0; q < HQ / 4; q++)
+    *reinterpret_cast<float4*>(out + (4 * q + k) * 4) = make_float4(tanhf(acc[4 * q]), tanhf(acc[4 * q + 1]), tanhf(acc[4 * q + 2]), tanhf(acc[4 * q + 3]));
 }
-// obs: this env's staged observation (shared memory), scratch: 2 x 64 floats of this env (shared memory)
+// w: the packed weights in shared memory; obs: this env's staged observation, scratch: 2 x 64 floats of this env (shared memory)
 template <int HQ>
-__device__ __forceinline__ float2 mlp_policy(const RollArgs& ra, int D, const float* __restrict__ obs, float* __restrict__ scratch, int k) {
+__device__ __forceinline__ float2 mlp_policy(const float* __restrict__ w, int D, const float* __restrict__ obs, float* __restrict__ scratch, int k) {
   constexpr int H = 4 * HQ;
-  const float* w1 = ra.w, *b1 = w1 + D * H, *w2 = b1 + H, *b2 = w2 + H * H, *w3 = b2 + H, *b3 = w3 + H * 8;
+  const float* w1 = w, *b1 = w1 + D * H, *w2 = b1 + H, *b2 = w2 + H * H, *w3 = b2 + H, *b3 = w3 + H * 8;
   mlp_layer<HQ>(w1, b1, D, obs, k, scratch);
   __syncwarp();
   mlp_layer<HQ>(w2, b2, H, scratch, k, scratch + 64);
   __syncwarp();
-  float2 o = __ldg(reinterpret_cast<const float2*>(b3 + 2 * k));
-#pragma unroll 4
+  float2 o = *reinterpret_cast<const float2*>(b3 + 2 * k);
+#pragma unroll 8
   for (int j = 0; j < H; j++) {
     const float xj = scratch[64 + j];
-    const float2 wv = __ldg(reinterpret_cast<const float2*>(w3 + j * 8 + 2 * k));
+    const float2 wv = *reinterpret_cast<const float2*>(w3 + j * 8 + 2 * k);
     o.x = fmaf(xj, wv.x, o.x); o.y = fmaf(xj, wv.y, o.y);
   }
   __syncwarp();
   return make_float2(tanhf(o.x), tanhf(o.y));
 }
+#define HRL_ROLL_WARPS 2                       // warps per CTA of the fused-rollout instantiations (they share the weights)
+#define HRL_MLP_MAX_FLOATS (60 * 64 + 64 + 64 * 64 + 64 + 64 * 8 + 8)   // obs_dim <= 60, H <= 64
 
 #ifdef HRL_DEBUG_CONTACTS
 __device__ float* g_dbg_contacts = nullptr;  // [N][4 legs][40]: candidate lists of the first sub-step of the last launch
 #endif
 
 template <int FAMILY, int SUB, int ROLL = 0>
-__global__ void __launch_bounds__(32 * HRL_WARPS_PER_CTA, Map<SUB>::MIN_CTAS)
+__global__ void __launch_bounds__(32 * (ROLL ? HRL_ROLL_WARPS : HRL_WARPS_PER_CTA), ROLL ? 2 : Map<SUB>::MIN_CTAS)
 ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float* __restrict__ bounds_g, int n_lines,
                const float* __restrict__ actions, const uint8_t* __restrict__ mask, float* __restrict__ obs_out_g,
                float* __restrict__ rew_out_g, uint8_t* __restrict__ done_out_g, float* __restrict__ info_out,
@@ -285,8 +291,15 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
   typedef Map<SUB> M;
   constexpr int LPE = M::LPE, EPW = M::EPW, IPL = M::IPL;
   // l: lane within the env, k: leg, sub: sub-lane of the leg (wide mappings), ew = es: env slot in the warp
+  constexpr int WPC = ROLL ? HRL_ROLL_WARPS : HRL_WARPS_PER_CTA;   // warps per CTA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l = lane & (LPE - 1), k = l & 3, sub = l >> 2, ew = lane / LPE, es = ew;
   float* rows = smem + warp * M::SMEM_FLOATS;
+  const float* wsm = smem + WPC * M::SMEM_FLOATS;   // ROLL: the policy weights, behind the warps' own regions
+  if (ROLL) {
+    const int nw = D * ra.H + ra.H + ra.H * ra.H + ra.H + ra.H * 8 + 8;
+    for (int i = threadIdx.x; i < nw; i += 32 * WPC) const_cast<float*>(wsm)[i] = __ldg(ra.w + i);
+    __syncthreads();
+  }
   float* cands = rows + M::ROWS_FLOATS + M::LAM_FLOATS;
   // the task layer runs after the last sub-step, when the solver rows are dead: its observation staging tile and
   // the sensor bins alias the row buffer (keeps a warp at < 37.8 KB so that 6 CTAs fit an SM at large batch sizes)
@@ -294,7 +307,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
   unsigned long long* sbins = (unsigned long long*)(rows + EPW * HRL_OBS_STAGE);   // [EPW][2][HRL_MAX_BINS]
   float* iscr = cands + M::CAND_FLOATS;  // cube-collider scratch: lives across the sub-steps
   const int N = cfg.num_envs, kind = cfg.env_kind;
-  const int env0 = (blockIdx.x * HRL_WARPS_PER_CTA + warp) * EPW;  // first env of this warp
+  const int env0 = (blockIdx.x * WPC + warp) * EPW;  // first env of this warp
   const int env_raw = env0 + ew;
   const bool active = env_raw < N;
   // the lane groups of a ragged tail shadow the last env (same trip counts, stores suppressed)
@@ -364,7 +377,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
     float2 a;
     if (ROLL) {  // the policy reads the observation the previous pass staged in shared memory (sobs is dense: [EPW][D])
       float* scr = cands + es * 128;
-      a = ra.H == 64 ? mlp_policy<16>(ra, D, sobs + es * D, scr, k) : mlp_policy<8>(ra, D, sobs + es * D, scr, k);
+      a = ra.H == 64 ? mlp_policy<16>(wsm, D, sobs + es * D, scr, k) : mlp_policy<8>(wsm, D, sobs + es * D, scr, k);
       if (ra.sigma > 0.f) {  // exploration noise: Box-Muller on the counter RNG, keyed by (seed, env), addressed by the env's step count
         float u[4];
         rng_u4(ra.seed, genv, STREAM_POLICY, (uint32_t)T.steps_total, (uint32_t)k, u);
@@ -836,7 +849,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
   }
 #ifdef HRL_WARP_TIMES
   if (st.wt && lane == 0) {
-    unsigned long long* w = st.wt + 4 * (size_t)(blockIdx.x * HRL_WARPS_PER_CTA + warp);
+    unsigned long long* w = st.wt + 4 * (size_t)(blockIdx.x * WPC + warp);
     w[0] = (unsigned long long)(clock64() - wt_t0); w[1] = (unsigned long long)(wt_t1 - wt_t0);
     w[2] = (unsigned long long)wt_trips; w[3] = (unsigned long long)(wt_passes | (wt_resets << 8));
   }
@@ -1371,9 +1384,12 @@ int hrl_create(const hrl_config* cfg, int32_t device, hrl_handle** out) {
   CKH(cudaFuncSetAttribute(ant_env_kernel<FAM, SUB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
   OPT_IN(0, 1); OPT_IN(1, 1); OPT_IN(0, 2); OPT_IN(1, 2); OPT_IN(0, 4); OPT_IN(1, 4);
 #undef OPT_IN
-  // the fused-rollout instantiations read their policy weights through L1: leave it room (no max-shared carve-out)
-  CKH(cudaFuncSetAttribute(ant_env_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HRL_WARPS_PER_CTA * Map<1>::SMEM_FLOATS * (int)sizeof(float)));
-  CKH(cudaFuncSetAttribute(ant_env_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HRL_WARPS_PER_CTA * Map<1>::SMEM_FLOATS * (int)sizeof(float)));
+  // the fused-rollout instantiations: 2 warps per CTA + the policy weights (<= 34 KB) in shared memory, 2 CTAs per SM
+  const int roll_smem = (HRL_ROLL_WARPS * Map<1>::SMEM_FLOATS + HRL_MLP_MAX_FLOATS) * (int)sizeof(float);
+  CKH(cudaFuncSetAttribute(ant_env_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, roll_smem));
+  CKH(cudaFuncSetAttribute(ant_env_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, roll_smem));
+  CKH(cudaFuncSetAttribute(ant_env_kernel<0, 1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CKH(cudaFuncSetAttribute(ant_env_kernel<1, 1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   h->sub = default_sub();
   // like the reference, reset() must be called before the first step(); an un-reset env has a
   // zero quaternion, produces a non-finite observation and is ended by the NaN guard
@@ -1561,8 +1577,9 @@ int hrl_rollout_mlp(hrl_handle* h, int32_t T, const float* d_weights, int32_t hi
   st.fin_flag = nullptr;
   RollArgs ra;
   ra.T = T; ra.H = hidden; ra.w = d_weights; ra.sigma = sigma; ra.seed = noise_seed; ra.act_out = d_act;
-  const int Tn = 32 * HRL_WARPS_PER_CTA, EPC = Map<1>::EPW * HRL_WARPS_PER_CTA, G = (h->N + EPC - 1) / EPC;
-  const size_t smem = (size_t)HRL_WARPS_PER_CTA * Map<1>::SMEM_FLOATS * sizeof(float);
+  const int Tn = 32 * HRL_ROLL_WARPS, EPC = Map<1>::EPW * HRL_ROLL_WARPS, G = (h->N + EPC - 1) / EPC;
+  const int nw = h->D * hidden + hidden + hidden * hidden + hidden + hidden * 8 + 8;
+  const size_t smem = ((size_t)HRL_ROLL_WARPS * Map<1>::SMEM_FLOATS + nw) * sizeof(float);
   cudaStream_t s = (cudaStream_t)stream;
   if (h->cfg.env_kind == HRL_ANT_GATHER)
     ant_env_kernel<0, 1, 1><<<G, Tn, smem, s>>>(h->cfg, st, h->d_bounds, h->n_lines, nullptr, nullptr, d_obs, d_rew, d_done, nullptr, nullptr, 0, 0, h->D, ra);
