@@ -60,6 +60,7 @@ struct hrl_handle {
   uint8_t* s_done;
   size_t s_out_bytes;
   int sub;        // lane mapping of the ant kernels: 1 = 4 lanes per env, 2 = 8, 4 = 16 (hrl_set_lanes_per_env)
+  int compact;    // 4-lane mapping with compact solver rows (7 CTAs per SM): chosen when that saves a wave of CTAs
   int host_mode;  // HRL_HOST_AUTO / HRL_HOST_COPY / HRL_HOST_ZEROCOPY
   unsigned int* h_flag;  // pinned host word polled by hrl_step_host (zero-copy mode)
   unsigned int seq;
@@ -201,6 +202,14 @@ struct Map : WideMap<SUB> {
   static constexpr int MIN_CTAS = (SUB == 4 ? 14 : 7) / HRL_WARPS_PER_CTA;  // all 4096 envs resident in one wave
 };
 template <>
+struct Map<0> {  // 4 lanes per env with COMPACT solver rows: 30.1 KB per warp, 7 CTAs per SM (batches larger than one wave)
+  static constexpr int LPE = 4, EPW = 8, IPL = 4, ROW_F4 = 3, ENV_F4 = HRL_ENV_F4_COMPACT;
+  static constexpr int ROWS_FLOATS = HRL_EPW * HRL_ENV_F4_COMPACT * 4, LAM_FLOATS = HRL_LAM_FLOATS_PER_WARP;
+  static constexpr int CAND_FLOATS = HRL_MAXC * HRL_CAND_F * 32, ITEM_FLOATS = HRL_ITEM_SCRATCH_FLOATS;
+  static constexpr int SMEM_FLOATS = ROWS_FLOATS + LAM_FLOATS + CAND_FLOATS + ITEM_FLOATS;
+  static constexpr int MIN_CTAS = 7 / HRL_WARPS_PER_CTA;
+};
+template <>
 struct Map<1> {
   static constexpr int LPE = 4, EPW = 8, IPL = 4, ROW_F4 = 4, ENV_F4 = HRL_ENV_F4;
   static constexpr int ROWS_FLOATS = HRL_ROWS_FLOATS_PER_WARP, LAM_FLOATS = HRL_LAM_FLOATS_PER_WARP;
@@ -210,7 +219,7 @@ struct Map<1> {
 };
 template <int SUB>
 constexpr bool tiles_fit() { return Map<SUB>::ROWS_FLOATS >= Map<SUB>::EPW * HRL_OBS_STAGE + 2 * Map<SUB>::EPW * 2 * HRL_MAX_BINS; }
-static_assert(tiles_fit<1>() && tiles_fit<2>() && tiles_fit<4>(), "task-layer tiles must fit in the row buffer");
+static_assert(tiles_fit<0>() && tiles_fit<1>() && tiles_fit<2>() && tiles_fit<4>(), "task-layer tiles must fit in the row buffer");
 
 // ------------------------------------------------------------------------------------------
 // fused rollout ("policy-inference fusion"): T steps in ONE launch, the actions of every step
@@ -401,8 +410,8 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
       const bool on = (i == 0) || !cfg.torque_first_substep_only;
       // cube colliders (FAMILY 0): the contact points of the LAST sub-step are what getContactPoints reports
       // (ant_gather_env.py:114)
-      if (SUB == 1)
-        ant_substep<FAMILY == 0>(s, P, lc, on ? tau1 : 0.f, on ? tau2 : 0.f, rows, cands, lane, k, es, feet_ground, sc, sl, it_x, it_y,
+      if (SUB <= 1)
+        ant_substep<FAMILY == 0, SUB == 0>(s, P, lc, on ? tau1 : 0.f, on ? tau2 : 0.f, rows, cands, lane, k, es, feet_ground, sc, sl, it_x, it_y,
                                  iscr, mode == 0 && i == ns - 1
 #if defined(HRL_WARP_TIMES) || defined(HRL_DEBUG_CONTACTS)
 #ifdef HRL_WARP_TIMES
@@ -1382,7 +1391,7 @@ int hrl_create(const hrl_config* cfg, int32_t device, hrl_handle** out) {
   CKH(cudaFuncSetAttribute(ant_env_kernel<FAM, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,                             \
                            HRL_WARPS_PER_CTA * Map<SUB>::SMEM_FLOATS * (int)sizeof(float)));                                  \
   CKH(cudaFuncSetAttribute(ant_env_kernel<FAM, SUB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
-  OPT_IN(0, 1); OPT_IN(1, 1); OPT_IN(0, 2); OPT_IN(1, 2); OPT_IN(0, 4); OPT_IN(1, 4);
+  OPT_IN(0, 0); OPT_IN(1, 0); OPT_IN(0, 1); OPT_IN(1, 1); OPT_IN(0, 2); OPT_IN(1, 2); OPT_IN(0, 4); OPT_IN(1, 4);
 #undef OPT_IN
   // the fused-rollout instantiations: 2 warps per CTA + the policy weights (<= 34 KB) in shared memory, 2 CTAs per SM
   const int roll_smem = (HRL_ROLL_WARPS * Map<1>::SMEM_FLOATS + HRL_MLP_MAX_FLOATS) * (int)sizeof(float);
@@ -1391,6 +1400,15 @@ int hrl_create(const hrl_config* cfg, int32_t device, hrl_handle** out) {
   CKH(cudaFuncSetAttribute(ant_env_kernel<0, 1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CKH(cudaFuncSetAttribute(ant_env_kernel<1, 1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   h->sub = default_sub();
+  {
+    // CTAs (= warps of 8 envs) per wave: 6 per SM with the 14-wide rows (37.5 KB), 7 with the compact ones (30.1 KB, ~7 %
+    // more solver instructions).  Compact pays when it saves a whole wave: e.g. 16 384 envs = 2048 CTAs = 3 waves vs 2.
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    const int ctas = (h->N + HRL_EPW - 1) / HRL_EPW, w6 = (ctas + 6 * n_sm - 1) / (6 * n_sm), w7 = (ctas + 7 * n_sm - 1) / (7 * n_sm);
+    h->compact = w7 < w6;
+    if (const char* e = getenv("HRL_B200_COMPACT")) h->compact = atoi(e) != 0;
+  }
   // like the reference, reset() must be called before the first step(); an un-reset env has a
   // zero quaternion, produces a non-finite observation and is ended by the NaN guard
   CKH(cudaDeviceSynchronize());
@@ -1424,6 +1442,7 @@ static int launch_env(hrl_handle* h, int mode, int n_sub, const float* act, cons
     const bool gather = h->cfg.env_kind == HRL_ANT_GATHER;
     if (h->sub == 4) { if (gather) LAUNCH(0, 4); else LAUNCH(1, 4); }
     else if (h->sub == 2) { if (gather) LAUNCH(0, 2); else LAUNCH(1, 2); }
+    else if (h->compact) { if (gather) LAUNCH(0, 0); else LAUNCH(1, 0); }
     else { if (gather) LAUNCH(0, 1); else LAUNCH(1, 1); }
 #undef LAUNCH
   }
