@@ -69,12 +69,13 @@ def peaks():
 
 
 def load_ref_pybullet_mp():
-    """bench/ref_pybullet_mp.py, loaded by path (a `bench` package would shadow this very file)."""
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("ref_pybullet_mp", os.path.join(ROOT, "bench", "ref_pybullet_mp.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod
+    """bench/ref_pybullet_mp.py.  Imported under its own top-level name (a `bench` package would shadow this very file);
+    its worker processes are spawned and must be able to import the module too, so its directory goes on sys.path."""
+    d = os.path.join(ROOT, "bench")
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    import ref_pybullet_mp
+    return ref_pybullet_mp
 
 
 def median(xs):
