@@ -57,6 +57,38 @@
 #define HRL_CAND_F 8
 #define HRL_SMEM_FLOATS_PER_WARP (HRL_ROWS_FLOATS_PER_WARP + HRL_LAM_FLOATS_PER_WARP + HRL_MAXC * HRL_CAND_F * 32)
 
+// ---- Delassus-space sweep (fast path of the 4-lane mapping; DESIGN.md "Round 2 - Delassus-space sweep") ----
+// When no env of the warp has more than 4 contacts in this sub-step (warp-uniform test; in the settled regime that is
+// every warp: 4 feet on the ground), the rows are NOT stored in visit order but TRANSPOSED into 24 static positions
+//   0-7 joint-limit rows (Bullet order), 8 + 4c + (0, 1, 2) normal / friction 1 / friction 2 of contact c (11 + 4c: pad)
+// and the sweep runs on the normalised Gram matrix What[i][j] = (a_i . a_j) / (a_j . a_j) (zero diagonal): per row it
+// tracks the unclamped target t_j = lambda_j + rhs'_j - (a_j . dv') / (a_j . a_j) in a register, so that a visit is
+// clamp(t_i) -> dl -> a few independent FMAs - no 14-term dot and no axpy on the dependency chain (the velocity-space
+// visit is dot -> fma -> max -> sub -> axpy, ~60 cycles of latency with one warp per scheduler).  The targets of the
+// 8 limit rows live redundantly in all 4 lanes of the env (a limit visit needs no communication); lane c OWNS contact c
+// (normal + friction pair: the pair visit finds lambda_n, both targets and mu in its own registers) and broadcasts its
+// impulse change with one shuffle.  Same iterates as the velocity-space sweep in exact arithmetic
+// (tests/test_delassus_form.py).  The buffers alias the env's row region (floats from its base); the zero rows of the
+// velocity-space path are re-zeroed when that path runs.
+// MEASURED AND NOT SHIPPED (-DHRL_DELASSUS=1 builds it; tools/gpu_ab_sweep.sh runs the A/B; all GPU parity tests green):
+// 51.1 us per step against 43.3 us for the velocity-space sweep at 4096 AntGather envs (a fully redundant variant, all 20
+// targets in every lane: 49.8 us).  The Gram matrix costs 13.6 k cycles per step and the shuffles put ~30 cycles of
+// latency on every contact visit - with one warp per scheduler nothing hides either (profiles/r2_delassus_*).
+#ifndef HRL_DELASSUS
+#define HRL_DELASSUS 0
+#endif
+#define HRL_DS_MAXC 4        // contacts per env the fast path holds (more: velocity-space sweep)
+#define HRL_DS_P 24          // positions
+#define HRL_DS_ROWS 20       // rows of What: limit p -> p, contact c direction d -> 8 + 3 c + d
+#define HRL_DS_AT 0          // [14][24] whitened rows, transposed: component m of position p at m * 24 + p
+#define HRL_DS_DINV 336      // [24] 1 / (a . a)
+#define HRL_DS_RHS 360       // [24] rhs / (a . a)
+#define HRL_DS_LEG 384       // [24] leg of the position's row (int)
+#define HRL_DS_ZERO_F4 104   // float4 cleared per env and sub-step: everything above, padded to 4 lanes x 26
+#define HRL_DS_W 416         // [20][24] What, row r at 416 + 24 r
+static_assert(HRL_DS_W + HRL_DS_ROWS * HRL_DS_P <= HRL_ROWS_ENV * 16, "Delassus buffers must fit in the env's row region");
+static_assert(HRL_MAXC >= 1 && HRL_DS_MAXC == 4, "one contact per lane");
+
 // food / poison cube colliders (hrl_config.item_contacts): per-warp scratch [EPW][16] (x, y) + [EPW][2] 64-bit words
 // holding 16 8-bit contact-point counters (13 spheres + 12 capsule cylinders can touch one cube)
 #define HRL_ITEM_SCRATCH_FLOATS (HRL_EPW * 16 * 2 + HRL_EPW * 4)
@@ -381,7 +413,8 @@ __device__ __noinline__ int capsules_vs_cubes(V3 O, V3 rh, V3 r_ank, V3 r_tip, u
 template <bool COMPACT = false>
 __device__ __forceinline__ void emit_row(float4* __restrict__ rb, int pos, int k,
                                          const LegDyn& D, const float JB[6], float j1, float j2, const float ub[6],
-                                         float u1, float u2, float pen, float erp, float inv_h, bool positional) {
+                                         float u1, float u2, float pen, float erp, float inv_h, bool positional,
+                                         bool fast = false, int slot = 0) {
   float Jt[6], z[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) Jt[i] = JB[i] - (D.K0[i] * j1 + D.K1[i] * j2);
@@ -401,6 +434,17 @@ __device__ __forceinline__ void emit_row(float4* __restrict__ rb, int pos, int k
   if (positional) {
     if (pen > 0.f) velErr -= pen * inv_h;
     else posErr = -pen * erp * inv_h;
+  }
+  if (!COMPACT && HRL_DELASSUS && fast) {  // transposed, into static position `slot` (cleared beforehand: the other legs' components stay 0)
+    float* f = reinterpret_cast<float*>(rb);
+#pragma unroll
+    for (int i = 0; i < 6; i++) f[HRL_DS_AT + i * HRL_DS_P + slot] = z[i];
+    f[HRL_DS_AT + (6 + 2 * k) * HRL_DS_P + slot] = y0;
+    f[HRL_DS_AT + (7 + 2 * k) * HRL_DS_P + slot] = y1;
+    f[HRL_DS_DINV + slot] = dinv;
+    f[HRL_DS_RHS + slot] = (posErr + velErr) * dinv;
+    reinterpret_cast<int*>(f)[HRL_DS_LEG + slot] = k;
+    return;
   }
   if (COMPACT) {
     float4* r = rb + pos * 3;
@@ -489,6 +533,181 @@ __device__ __forceinline__ void pair_visit(float4* __restrict__ cp, float2 dv[7]
   na = on ? na * sc : c.x; nb = on ? nb * sc : c.y;
   *reinterpret_cast<float2*>(cp) = make_float2(na, nb);
   axpy14(dv, A.p, na - c.x); axpy14(dv, B.p, nb - c.y);
+}
+
+// ---- Delassus-space sweep: helpers (positions and layout at the top of this file) ----
+// Sweep state of one lane: targets / impulses of the 8 limit rows (the same in the 4 lanes of the env) and of the
+// lane's own contact (x normal, y friction 1, z friction 2, w pad).
+struct DsState {
+  float2 tL[4], lL[4];
+  float4 tC, lC;
+  float mu;
+};
+template <int S>
+__device__ __forceinline__ float& ds_at(float2 a[4]) { return (S & 1) ? a[S >> 1].y : a[S >> 1].x; }
+// t_j -= What[r][j] * dl: the 8 limit targets (2 broadcast LDS.128) and the lane's own contact (1 LDS.128)
+__device__ __forceinline__ void ds_apply(DsState& st, const float* __restrict__ W, int r, int k, float dl) {
+  const float4* __restrict__ w = reinterpret_cast<const float4*>(W + r * HRL_DS_P);
+  const float2 d = make_float2(-dl, -dl);
+  const float4 q0 = w[0], q1 = w[1], qc = w[2 + k];
+  st.tL[0] = fma2(make_float2(q0.x, q0.y), d, st.tL[0]);
+  st.tL[1] = fma2(make_float2(q0.z, q0.w), d, st.tL[1]);
+  st.tL[2] = fma2(make_float2(q1.x, q1.y), d, st.tL[2]);
+  st.tL[3] = fma2(make_float2(q1.z, q1.w), d, st.tL[3]);
+  float2 a = make_float2(st.tC.x, st.tC.y), b = make_float2(st.tC.z, st.tC.w);
+  a = fma2(make_float2(qc.x, qc.y), d, a);
+  b = fma2(make_float2(qc.z, qc.w), d, b);
+  st.tC = make_float4(a.x, a.y, b.x, b.y);
+}
+// joint-limit row S: every lane holds its target, no communication
+template <int S>
+__device__ __forceinline__ void ds_limit(DsState& st, const float* __restrict__ W, int k, float hi) {
+  float& lam = ds_at<S>(st.lL);
+  const float nl = fminf(fmaxf(ds_at<S>(st.tL), 0.f), hi);
+  const float dl = nl - lam;
+  lam = nl;
+  ds_apply(st, W, S, k, dl);
+}
+// normal of contact C: lane C computes, one shuffle tells the others
+template <int C>
+__device__ __forceinline__ void ds_normal(DsState& st, const float* __restrict__ W, int k) {
+  const float nl = fmaxf(st.tC.x, 0.f);
+  const float dl = __shfl_sync(HRL_FULL_MASK, nl - st.lC.x, C, 4);
+  if (k == C) st.lC.x = nl;
+  ds_apply(st, W, 8 + 3 * C, k, dl);
+}
+// friction pair of contact C with the implicit cone |f| <= mu * lambda_n; kept as it is while lambda_n = 0 (pair_visit)
+template <int C>
+__device__ __forceinline__ void ds_pair(DsState& st, const float* __restrict__ W, int k) {
+  float na = st.tC.y, nb = st.tC.z;
+  const float lim = st.mu * st.lC.x, len2 = fmaf(na, na, nb * nb);
+  const float sc = (len2 > lim * lim) ? lim * rsqrt_ftz(fmaxf(len2, 1e-30f)) : 1.f;
+  const bool on = st.lC.x > 0.f;
+  na = on ? na * sc : st.lC.y; nb = on ? nb * sc : st.lC.z;
+  const float dla = __shfl_sync(HRL_FULL_MASK, na - st.lC.y, C, 4), dlb = __shfl_sync(HRL_FULL_MASK, nb - st.lC.z, C, 4);
+  if (k == C) { st.lC.y = na; st.lC.z = nb; }
+  ds_apply(st, W, 9 + 3 * C, k, dla);
+  ds_apply(st, W, 10 + 3 * C, k, dlb);
+}
+// the 3 rows of one contact (same leg: lrc = that leg's two components of AT) against the 4 columns of group g:
+// acc[i] = sum_m a_i[m] * AT[m][4g .. 4g+3] - 8 broadcast LDS.128 feed 48 FFMA2 in 6 independent chains
+__device__ __forceinline__ void ds_gram_group3(const float* __restrict__ f, const float2 (*zz)[8], const float* __restrict__ lrc, int g,
+                                               float2 (*acc)[2]) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) { acc[i][0] = make_float2(0.f, 0.f); acc[i][1] = make_float2(0.f, 0.f); }
+#pragma unroll
+  for (int m = 0; m < 8; m++) {
+    const float4 w = *reinterpret_cast<const float4*>((m < 6 ? f + HRL_DS_AT + m * HRL_DS_P : lrc + (m - 6) * HRL_DS_P) + 4 * g);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      acc[i][0] = fma2(zz[i][m], make_float2(w.x, w.y), acc[i][0]);
+      acc[i][1] = fma2(zz[i][m], make_float2(w.z, w.w), acc[i][1]);
+    }
+  }
+}
+// What from the transposed rows.  Lane k computes the 3 rows of contact k against all columns (and, transposed, the
+// contact's columns of the limit rows: What[j][c] = W[c][j] / diag_c), then limit rows k and k + 4 against the limit columns.
+// gmask: warp-uniform mask of the column groups that hold a row in ANY env of the warp (0: limits 0-3, 1: limits 4-7, 2 + c: contact c).
+__device__ __forceinline__ void ds_gram(float* __restrict__ f, int k, unsigned gmask) {
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (gmask & ~3u) {  // ---- contact rows
+    const int p0 = 8 + 4 * k;
+    const int leg = reinterpret_cast<const int*>(f)[HRL_DS_LEG + p0];
+    const float* lrc = f + HRL_DS_AT + (6 + 2 * leg) * HRL_DS_P;
+    float2 zz[3][8];
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+      const float4 v = *reinterpret_cast<const float4*>((m < 6 ? f + HRL_DS_AT + m * HRL_DS_P : lrc + (m - 6) * HRL_DS_P) + p0);
+      zz[0][m] = make_float2(v.x, v.x); zz[1][m] = make_float2(v.y, v.y); zz[2][m] = make_float2(v.z, v.z);
+    }
+    const float4 dme = *reinterpret_cast<const float4*>(f + HRL_DS_DINV + p0);  // 1 / diag of this contact's rows
+    float4* __restrict__ wout = reinterpret_cast<float4*>(f + HRL_DS_W + (8 + 3 * k) * HRL_DS_P);
+#pragma unroll 1
+    for (int g = 0; g < HRL_DS_P / 4; g++) {
+      if (!((gmask >> g) & 1u)) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) wout[i * (HRL_DS_P / 4) + g] = zero4;
+        if (g < 2) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) *reinterpret_cast<float4*>(f + HRL_DS_W + (4 * g + j) * HRL_DS_P + p0) = zero4;
+        }
+        continue;
+      }
+      float2 acc[3][2];
+      ds_gram_group3(f, zz, lrc, g, acc);
+      if (g < 2) {  // transposed: the limit rows' columns of this contact
+        const float wj[3][4] = {{acc[0][0].x, acc[0][0].y, acc[0][1].x, acc[0][1].y}, {acc[1][0].x, acc[1][0].y, acc[1][1].x, acc[1][1].y},
+                                {acc[2][0].x, acc[2][0].y, acc[2][1].x, acc[2][1].y}};
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          *reinterpret_cast<float4*>(f + HRL_DS_W + (4 * g + j) * HRL_DS_P + p0) = make_float4(wj[0][j] * dme.x, wj[1][j] * dme.y, wj[2][j] * dme.z, 0.f);
+      }
+      const float4 d = *reinterpret_cast<const float4*>(f + HRL_DS_DINV + 4 * g);
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        acc[i][0] = mul2(acc[i][0], make_float2(d.x, d.y)); acc[i][1] = mul2(acc[i][1], make_float2(d.z, d.w));
+      }
+      if (g == 2 + k) { acc[0][0].x = 0.f; acc[1][0].y = 0.f; acc[2][1].x = 0.f; }  // zero diagonal
+#pragma unroll
+      for (int i = 0; i < 3; i++) wout[i * (HRL_DS_P / 4) + g] = make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
+    }
+  } else if (gmask & 3u) {  // no contact anywhere in the warp: the limit rows' contact columns are never used, but must be finite
+#pragma unroll
+    for (int j = 0; j < 8; j++) *reinterpret_cast<float4*>(f + HRL_DS_W + j * HRL_DS_P + 8 + 4 * k) = zero4;
+  }
+  if (gmask & 3u) {  // ---- limit rows k and k + 4 against the limit columns
+    const int leg0 = reinterpret_cast<const int*>(f)[HRL_DS_LEG + k], leg1 = reinterpret_cast<const int*>(f)[HRL_DS_LEG + 4 + k];
+    const float* const lr[2] = {f + HRL_DS_AT + (6 + 2 * leg0) * HRL_DS_P, f + HRL_DS_AT + (6 + 2 * leg1) * HRL_DS_P};
+    float2 zz[2][8];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+      for (int m = 0; m < 8; m++) {
+        const float v = (m < 6 ? f + HRL_DS_AT + m * HRL_DS_P : lr[i] + (m - 6) * HRL_DS_P)[4 * i + k];
+        zz[i][m] = make_float2(v, v);
+      }
+#pragma unroll 1
+    for (int g = 0; g < 2; g++) {
+      float4* __restrict__ w0 = reinterpret_cast<float4*>(f + HRL_DS_W + k * HRL_DS_P) + g;
+      float4* __restrict__ w1 = reinterpret_cast<float4*>(f + HRL_DS_W + (4 + k) * HRL_DS_P) + g;
+      if (!((gmask >> g) & 1u)) { *w0 = zero4; *w1 = zero4; continue; }
+      float2 acc[2][2];
+      // (two different legs: the leg part of each row reads its own two components)
+#pragma unroll
+      for (int i = 0; i < 2; i++) { acc[i][0] = make_float2(0.f, 0.f); acc[i][1] = make_float2(0.f, 0.f); }
+#pragma unroll
+      for (int m = 0; m < 8; m++) {
+        if (m < 6) {  // base components: one load feeds both rows; leg components: per row
+          const float4 w = *reinterpret_cast<const float4*>(f + HRL_DS_AT + m * HRL_DS_P + 4 * g);
+#pragma unroll
+          for (int i = 0; i < 2; i++) {
+            acc[i][0] = fma2(zz[i][m], make_float2(w.x, w.y), acc[i][0]);
+            acc[i][1] = fma2(zz[i][m], make_float2(w.z, w.w), acc[i][1]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 2; i++) {
+            const float4 w = *reinterpret_cast<const float4*>(lr[i] + (m - 6) * HRL_DS_P + 4 * g);
+            acc[i][0] = fma2(zz[i][m], make_float2(w.x, w.y), acc[i][0]);
+            acc[i][1] = fma2(zz[i][m], make_float2(w.z, w.w), acc[i][1]);
+          }
+        }
+      }
+      const float4 d = *reinterpret_cast<const float4*>(f + HRL_DS_DINV + 4 * g);
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        acc[i][0] = mul2(acc[i][0], make_float2(d.x, d.y)); acc[i][1] = mul2(acc[i][1], make_float2(d.z, d.w));
+        if (g == i) {  // zero diagonal: row 4 i + k, column k of group i
+          if (k == 0) acc[i][0].x = 0.f;
+          if (k == 1) acc[i][0].y = 0.f;
+          if (k == 2) acc[i][1].x = 0.f;
+          if (k == 3) acc[i][1].y = 0.f;
+        }
+      }
+      *w0 = make_float4(acc[0][0].x, acc[0][0].y, acc[0][1].x, acc[0][1].y);
+      *w1 = make_float4(acc[1][0].x, acc[1][0].y, acc[1][1].x, acc[1][1].y);
+    }
+  }
 }
 
 // One internal step of h = dt/substeps.  `rows`/`cands` point at this WARP's shared memory
@@ -761,6 +980,19 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
   }
   const int tot = __shfl_sync(HRL_FULL_MASK, incl, 3, 4);
   const int offL = (incl & 0xff) - nL, offC = (incl >> 8) - nC, NL = tot & 0xff, NC = tot >> 8;
+  const int maxNL = __reduce_max_sync(HRL_FULL_MASK, NL), maxNC = __reduce_max_sync(HRL_FULL_MASK, NC);
+  // warp-uniform choice of the sweep: Delassus space (static slots, rows transposed) or velocity space (any row count)
+  const bool fast = !COMPACT && HRL_DELASSUS && maxNC <= HRL_DS_MAXC;
+  if (!COMPACT && HRL_DELASSUS) {
+    if (fast) {  // clear the transposed rows, 1 / diag, rhs, leg of all 20 slots: idle slots and the other legs' components are 0
+#pragma unroll
+      for (int i = 0; i < HRL_DS_ZERO_F4 / 4; i++) rb[4 * i + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {     // the Delassus buffers of an earlier sub-step overlap the two all-zero rows of the idle visits
+      rb[HRL_ROW_ZERO * 4 + 2 * k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[HRL_ROW_ZERO * 4 + 2 * k + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+  }
   {
     const float zero6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -771,7 +1003,7 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
       const float sg = lo ? 1.f : -1.f, pen = lo ? pl : ph;
       const int pos = offL + (jj ? (int)lim1 : 0);
       lamL[pos] = 0.f;
-      emit_row<COMPACT>(rb, pos, k, D, zero6, jj ? 0.f : sg, jj ? sg : 0.f, ub, u1, u2, pen, P.erp_l, inv_h, true);
+      emit_row<COMPACT>(rb, pos, k, D, zero6, jj ? 0.f : sg, jj ? sg : 0.f, ub, u1, u2, pen, P.erp_l, inv_h, true, fast, pos);
     }
   }
   for (int c = 0; c < nC; c++) {
@@ -793,7 +1025,8 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
       const float j1 = body >= 1.f ? dot(a1, cross(Ph, d)) : 0.f;
       const float j2 = body >= 2.f ? dot(a2, cross(Pa, d)) : 0.f;
       const int pos = di == 0 ? HRL_ROW_NRM_LAST - ci : HRL_ROW_FRI0 + 2 * ci + (di - 1);
-      emit_row<COMPACT>(rb, pos, k, D, JB, j1, j2, ub, u1, u2, dist, P.erp_c, inv_h, di == 0);
+      emit_row<COMPACT>(rb, pos, k, D, JB, j1, j2, ub, u1, u2, dist, P.erp_c, inv_h, di == 0, fast,
+                        8 + 4 * ci + di);
     }
   }
   stat_contacts += nC; stat_limits += nL;
@@ -804,11 +1037,88 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
   // dependency chain).  A single warp issues at most one instruction per ~2 cycles, so the sweep is
   // bound by its instruction count: packed FFMA2 arithmetic, rows prefetched one visit ahead into
   // ping-pong registers, trip counts = maxima over the envs of the warp, idle visits on a zero row.
+  if (trips) *trips += maxNL + (maxNC << 16);  // profiling builds (HRL_WARP_TIMES): the warp's solver trip counts
+  float dvp[6], gp0, gp1;  // solver result in the transformed velocity: base part, this leg's part
+  if (!COMPACT && HRL_DELASSUS && fast) {
+    // ---------------- Delassus-space sweep (layout and derivation at the top of this file) ----------------
+    float* __restrict__ f = reinterpret_cast<float*>(rb);
+    const unsigned gmask = (maxNL > 0 ? 1u : 0u) | (maxNL > 4 ? 2u : 0u) | (maxNC > 0 ? 4u : 0u) | (maxNC > 1 ? 8u : 0u) |
+                           (maxNC > 2 ? 16u : 0u) | (maxNC > 3 ? 32u : 0u);
+    ds_gram(f, k, gmask);
+    DsState st;
+    {  // lambda = 0, dv' = 0: t = rhs'
+      const float4 q0 = *reinterpret_cast<const float4*>(f + HRL_DS_RHS), q1 = *reinterpret_cast<const float4*>(f + HRL_DS_RHS + 4);
+      st.tL[0] = make_float2(q0.x, q0.y); st.tL[1] = make_float2(q0.z, q0.w); st.tL[2] = make_float2(q1.x, q1.y); st.tL[3] = make_float2(q1.z, q1.w);
+      st.tC = *reinterpret_cast<const float4*>(f + HRL_DS_RHS + 8 + 4 * k);
+#pragma unroll
+      for (int i = 0; i < 4; i++) st.lL[i] = make_float2(0.f, 0.f);
+      st.lC = make_float4(0.f, 0.f, 0.f, 0.f);
+      st.mu = cl[k].w;
+    }
+    __syncwarp();  // What complete
+    const float* __restrict__ W = f + HRL_DS_W;
+#define HRL_DS_L(S) ds_limit<S>(st, W, k, P.max_imp)
+#pragma unroll 1
+    for (int it = 0; it < P.iters; it++) {
+      // (1) joint-limit rows, backwards on even iterations (idle positions between an env's rows are no-ops: t = lambda = 0)
+      if (it & 1) {
+        if (maxNL > 0) { HRL_DS_L(0); HRL_DS_L(1); }
+        if (maxNL > 2) { HRL_DS_L(2); HRL_DS_L(3); }
+        if (maxNL > 4) { HRL_DS_L(4); HRL_DS_L(5); }
+        if (maxNL > 6) { HRL_DS_L(6); HRL_DS_L(7); }
+      } else {
+        switch (maxNL) {
+          case 8: HRL_DS_L(7);
+          case 7: HRL_DS_L(6);
+          case 6: HRL_DS_L(5);
+          case 5: HRL_DS_L(4);
+          case 4: HRL_DS_L(3);
+          case 3: HRL_DS_L(2);
+          case 2: HRL_DS_L(1);
+          case 1: HRL_DS_L(0);
+          default: break;
+        }
+      }
+      // (2) contact normals, (3) friction pairs (idle contacts are no-ops - t = lambda = 0, What row 0 - so whole blocks
+      // run without exits in between)
+      if (maxNC > 0) {
+        ds_normal<0>(st, W, k); ds_normal<1>(st, W, k);
+        if (maxNC > 2) { ds_normal<2>(st, W, k); ds_normal<3>(st, W, k); }
+        ds_pair<0>(st, W, k); ds_pair<1>(st, W, k);
+        if (maxNC > 2) { ds_pair<2>(st, W, k); ds_pair<3>(st, W, k); }
+      }
+    }
+#undef HRL_DS_L
+    // dv' = sum_p lambda_p a_p: the 6 base components and the 2 of this lane's leg
+    float2 lam[HRL_DS_P / 2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) lam[i] = st.lL[i];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      lam[4 + 2 * c] = make_float2(__shfl_sync(HRL_FULL_MASK, st.lC.x, c, 4), __shfl_sync(HRL_FULL_MASK, st.lC.y, c, 4));
+      lam[5 + 2 * c] = make_float2(__shfl_sync(HRL_FULL_MASK, st.lC.z, c, 4), 0.f);
+    }
+    float o[8];
+#pragma unroll
+    for (int mm = 0; mm < 8; mm++) {
+      const float4* __restrict__ a = reinterpret_cast<const float4*>(f + HRL_DS_AT + (mm < 6 ? mm : 2 * k + mm) * HRL_DS_P);
+      float2 s0 = make_float2(0.f, 0.f), s1 = s0;
+#pragma unroll
+      for (int g = 0; g < HRL_DS_P / 4; g++) {
+        const float4 q = a[g];
+        s0 = fma2(make_float2(q.x, q.y), lam[2 * g], s0);
+        s1 = fma2(make_float2(q.z, q.w), lam[2 * g + 1], s1);
+      }
+      s0 = add2(s0, s1);
+      o[mm] = s0.x + s0.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) dvp[i] = o[i];
+    gp0 = o[6]; gp1 = o[7];
+  } else {
   float2 dv[7];
 #pragma unroll
   for (int i = 0; i < 7; i++) dv[i] = make_float2(0.f, 0.f);
-  const int maxNL = __reduce_max_sync(HRL_FULL_MASK, NL), maxNC = __reduce_max_sync(HRL_FULL_MASK, NC);
-  if (trips) *trips += maxNL + (maxNC << 16);  // profiling builds (HRL_WARP_TIMES): the warp's solver trip counts
 #define HRL_LIM_ROW(t) (((t) < NL) ? lbase + lstep * (t) : HRL_ROW_ZERO)
 #define HRL_LIM_LAM(t, r) (lamL + (((t) < NL) ? (r) : 8))
 #define HRL_SLOT(t) (((t) < NC) ? (t) : HRL_NSLOT)
@@ -864,6 +1174,11 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
 #undef HRL_LIM_LAM
 #undef HRL_SLOT
 #undef HRL_LIM_ROW
+#pragma unroll
+  for (int j = 0; j < 6; j++) dvp[j] = (j & 1) ? dv[j >> 1].y : dv[j >> 1].x;
+  const float2 gp = k == 0 ? dv[3] : (k == 1 ? dv[4] : (k == 2 ? dv[5] : dv[6]));
+  gp0 = gp.x; gp1 = gp.y;
+  }
   __syncwarp();
 
   // ---------------- back to physical velocities, clamp, integrate ----------------
@@ -872,11 +1187,9 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
   for (int i = 0; i < 6; i++) {  // dvb = L^-T dvb'
     float a = 0.f;
 #pragma unroll
-    for (int j = i; j < 6; j++) a = fmaf(D.Li[j * (j + 1) / 2 + i], (j & 1) ? dv[j >> 1].y : dv[j >> 1].x, a);
+    for (int j = i; j < 6; j++) a = fmaf(D.Li[j * (j + 1) / 2 + i], dvp[j], a);
     dvb[i] = a;
   }
-  const float2 gp = k == 0 ? dv[3] : (k == 1 ? dv[4] : (k == 2 ? dv[5] : dv[6]));
-  const float gp0 = gp.x, gp1 = gp.y;
   const float g2 = gp1 * D.il22, g1 = (gp0 - D.l21 * g2) * D.il11;  // g = Ll^-T g'
   float dq1 = g1, dq2 = g2;
 #pragma unroll

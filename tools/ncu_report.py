@@ -28,9 +28,11 @@ def regions():
     def L(src, pat):
         return next(i for i, l in enumerate(src) if pat in l) + 1
     marks = [("fk", "LegKin leg_fk("), (None, "constexpr int sym6"), ("sinv_mul", "void sinv_mul("), (None, "float clampf("),
-             ("emit_row", "void emit_row("), ("pgs_helpers", "Blackwell packed fp32"), (None, "void ant_substep("),
+             ("emit_row", "void emit_row("), ("pgs_helpers", "Blackwell packed fp32"),
+             ("ds_helpers", "// ---- Delassus-space sweep: helpers"), (None, "void ant_substep("),
              ("contacts_detect", "contacts: spheres vs"), ("dynamics", "smooth dynamics: bias"),
              ("rows_build", "constraint rows: counts"), ("pgs", "// ---------------- projected Gauss-Seidel, Bullet"),
+             ("ds_sweep", "Delassus-space sweep (layout and derivation"), ("pgs_vel", "  float2 dv[7];"),
              ("integrate", "back to physical velocities")]
     pos = [(n, L(ant, p)) for n, p in marks] + [(None, len(ant) + 1)]
     out = [("hrl_ant.cuh", lo, hi - 1, n) for (n, lo), (_, hi) in zip(pos, pos[1:]) if n]
