@@ -233,6 +233,7 @@ __device__ __noinline__ float2 quat_exp_literal(float w2, float h) {
 }
 // Append one contact candidate of this lane (contact point on the robot relative to O, normal, distance, body).
 __device__ __forceinline__ int add_cand(float* __restrict__ cands, int lane, int nC, V3 crel, float r, V3 n, float dist, float body) {
+  HRL_CHECK(nC >= 0 && nC <= HRL_MAXC && lane >= 0 && lane < 32);
   if (nC < HRL_MAXC) {
     const V3 Prel = crel - r * n;
     CAND(nC, 0) = Prel.x; CAND(nC, 1) = Prel.y; CAND(nC, 2) = Prel.z;
@@ -415,6 +416,8 @@ __device__ __forceinline__ void emit_row(float4* __restrict__ rb, int pos, int k
                                          const LegDyn& D, const float JB[6], float j1, float j2, const float ub[6],
                                          float u1, float u2, float pen, float erp, float inv_h, bool positional,
                                          bool fast = false, int slot = 0) {
+  HRL_CHECK(fast || (pos >= 0 && pos < HRL_ROWS_ENV && pos != HRL_ROW_ZERO && pos != HRL_ROW_ZERO + 1));
+  HRL_CHECK(!fast || (slot >= 0 && slot < HRL_DS_P));
   float Jt[6], z[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) Jt[i] = JB[i] - (D.K0[i] * j1 + D.K1[i] * j2);
@@ -482,6 +485,7 @@ struct Row { float2 p[7]; float dinv, rhs; };  // a[0..13] as 7 pairs, 1/diag, r
 template <bool COMPACT = false>
 __device__ __forceinline__ Row ld_row(const float4* __restrict__ rb, int r) {
   Row R;
+  HRL_CHECK(r >= 0 && r < HRL_ROWS_ENV);
   if (COMPACT) {
     const float4 q0 = rb[r * 3], q1 = rb[r * 3 + 1], q2 = rb[r * 3 + 2];
     const int leg = __float_as_int(q2.z);
@@ -748,6 +752,7 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         const int gi = 4 * k + i;
+        HRL_CHECK(es >= 0 && es < HRL_EPW && gi < 16);
         const float dx = it_x[i] - s.O.x, dy = it_y[i] - s.O.y;
         if (gi < P.n_items && dx * dx + dy * dy < reach * reach) imask |= 1u << gi;
         ixy[2 * gi] = it_x[i]; ixy[2 * gi + 1] = it_y[i];
@@ -1002,6 +1007,7 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
       const bool lo = pl <= 0.f;
       const float sg = lo ? 1.f : -1.f, pen = lo ? pl : ph;
       const int pos = offL + (jj ? (int)lim1 : 0);
+      HRL_CHECK(pos >= 0 && pos < 8);
       lamL[pos] = 0.f;
       emit_row<COMPACT>(rb, pos, k, D, zero6, jj ? 0.f : sg, jj ? sg : 0.f, ub, u1, u2, pen, P.erp_l, inv_h, true, fast, pos);
     }
@@ -1016,6 +1022,7 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
     plane_space(n, t1, t2);
     const V3 Ph = Pr - K.rh, Pa = Pr - r_ank;
     const int ci = offC + c;
+    HRL_CHECK(ci >= 0 && ci < HRL_NSLOT && c < HRL_MAXC);
     cl[ci] = make_float4(0.f, 0.f, 0.f, cube ? P.mu_item : P.mu);
 #pragma unroll 1
     for (int di = 0; di < 3; di++) {
@@ -1122,6 +1129,7 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
 #define HRL_LIM_ROW(t) (((t) < NL) ? lbase + lstep * (t) : HRL_ROW_ZERO)
 #define HRL_LIM_LAM(t, r) (lamL + (((t) < NL) ? (r) : 8))
 #define HRL_SLOT(t) (((t) < NC) ? (t) : HRL_NSLOT)
+  HRL_CHECK(NL >= 0 && NL <= 8 && NC >= 0 && NC <= HRL_NSLOT && maxNL <= 8 && maxNC <= HRL_NSLOT);
   for (int it = 0; it < P.iters; it++) {
     // (1) joint-limit rows; Bullet walks the non-contact rows backwards on even iterations.
     // Two visits per trip (ping-pong row registers, next row prefetched), odd tail handled apart.

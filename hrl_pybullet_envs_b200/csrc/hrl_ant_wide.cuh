@@ -330,6 +330,7 @@ __device__ __forceinline__ void leg_dynamics_w(const AntLane& s, const SubstepPa
 // Whiten one constraint row of leg k (see emit_row of hrl_ant.cuh) and store it 8 wide at visit position `pos`.
 __device__ __forceinline__ void emit_row_w(float4* __restrict__ rb, int pos, int k, const LegDyn& D, const float JB[6], float j1, float j2,
                                            const float ub[6], float u1, float u2, float pen, float erp, float inv_h, bool positional) {
+  HRL_CHECK(pos >= 0 && pos < HRL_ROWS_ENV && pos != HRL_ROW_ZERO && pos != HRL_ROW_ZERO + 1);
   float Jt[6], z[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) Jt[i] = JB[i] - (D.K0[i] * j1 + D.K1[i] * j2);

@@ -310,6 +310,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
     __syncthreads();
   }
   float* cands = rows + M::ROWS_FLOATS + M::LAM_FLOATS;
+  HRL_CHECK(D > 0 && D <= HRL_OBS_STAGE && n_lines >= 0 && 4 * n_lines <= 32 && cfg.n_bins <= HRL_MAX_BINS && cfg.n_food + cfg.n_poison <= 16);
   // the task layer runs after the last sub-step, when the solver rows are dead: its observation staging tile and
   // the sensor bins alias the row buffer (keeps a warp at < 37.8 KB so that 6 CTAs fit an SM at large batch sizes)
   float* sobs = rows;                                                                   // [EPW][HRL_OBS_STAGE]
@@ -545,7 +546,15 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
         cos_t = (dx * cyw + dy * syw) * iw; sin_t = (dy * cyw - dx * syw) * iw;
       } else { cos_t = cyw; sin_t = -syw; }
     }
+#ifdef HRL_BOUNDS
+    struct ObsRow {  // HRL_BOUNDS builds: every index into the staging row is asserted
+      float* p; int n;
+      __device__ float& operator[](int i) const { assert(i >= 0 && i < n); return p[i]; }
+    };
+    const ObsRow so = {sobs + es * D, D};
+#else
     float* so = sobs + es * D;  // dense staging: the warp's observations are one contiguous span
+#endif
     const bool commit = (todo == 1);
     int fin = 1;       // finite flag (this lane's values)
     int switched = 0;  // Flagrun: the target changed in this step
@@ -593,6 +602,7 @@ ant_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const float*
           if (gi >= cfg.n_food + cfg.n_poison) continue;
           double d2;
           const int b = gather_item_bin(s.O.x, s.O.y, yaw, it_x[i], it_y[i], nb, cfg.sensor_range, cfg.sensor_span, &d2);
+          HRL_CHECK(b < nb && nb <= HRL_MAX_BINS);
           if (b >= 0) atomicMin(&sbins[(es * 2 + (gi < cfg.n_food ? 0 : 1)) * HRL_MAX_BINS + b], (unsigned long long)__double_as_longlong(d2));
         }
         __syncwarp();
@@ -1000,6 +1010,7 @@ point_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const floa
     if (work && has_item) {
       double d2;
       const int b = gather_item_bin(pos.x, pos.y, 0.f, it.x, it.y, nb, cfg.sensor_range, cfg.sensor_span, &d2);
+      HRL_CHECK(b < HRL_MAX_BINS && eb >= 0 && eb < HRL_POINT_EPB);
       if (b >= 0) atomicMin(&sb[eb][j < cfg.n_food ? 0 : 1][b], (unsigned long long)__double_as_longlong(d2));
     }
     __syncwarp();
@@ -1035,6 +1046,7 @@ point_env_kernel(const __grid_constant__ hrl_config cfg, DevState st, const floa
       const int keep_f = min(nb, cfg.n_food), keep_p = min(nb, cfg.n_poison);
       if (has_item && rank < (poison ? keep_p : keep_f)) {
         const int at = 8 + (poison ? 2 * keep_f : 0) + 2 * rank;
+        HRL_CHECK(at >= 0 && at + 1 < 8 + 2 * HRL_MAX_BINS && at + 1 < D);
         sobs[eb][at] = it.x; sobs[eb][at + 1] = it.y;
       }
     }
@@ -1146,6 +1158,7 @@ __global__ void gather_sensor_kernel(int M, int n_bins, float range, float span,
     double d2;
     b = gather_item_bin(xy[2 * m], xy[2 * m + 1], yaw[m], items[(m * 16 + gi) * 2], items[(m * 16 + gi) * 2 + 1], n_bins, range, span, &d2);
     if (bins) bins[m * 16 + gi] = b;
+    HRL_CHECK(b < HRL_MAX_BINS && b < n_bins);
     if (b >= 0) atomicMin(&sb[warp][half][(gi < 8 ? 0 : HRL_MAX_BINS) + b], (unsigned long long)__double_as_longlong(d2));
   }
   __syncwarp();
@@ -1187,7 +1200,11 @@ const char* hrl_last_error(void) { return g_err; }
 #define HRL_STR2(x) #x
 #define HRL_STR(x) HRL_STR2(x)
 const char* hrl_version(void) {
-  return "hrl_b200 0.2 (sm_100a; 4 lanes/env; " HRL_STR(HRL_ENVS_PER_WARP) " envs/warp; " HRL_STR(HRL_WARPS_PER_CTA) " warps/CTA; MAXC=" HRL_STR(HRL_MAXC) ")";
+  return "hrl_b200 0.2 (sm_100a; 4 lanes/env; " HRL_STR(HRL_ENVS_PER_WARP) " envs/warp; " HRL_STR(HRL_WARPS_PER_CTA) " warps/CTA; MAXC=" HRL_STR(HRL_MAXC)
+#ifdef HRL_BOUNDS
+         "; HRL_BOUNDS: device-side index asserts"
+#endif
+         ")";
 }
 int64_t hrl_launch_count(void) { return (int64_t)g_launches.load(); }
 

@@ -5,6 +5,15 @@
 
 #define HRL_FULL_MASK 0xffffffffu
 
+// -DHRL_BOUNDS=1 (libhrl_b200_chk.so, tests/test_gpu_bounds_build.py): device-side asserts on every computed index into the
+// shared-memory row / impulse / candidate / staging buffers - compute-sanitizer is not available on the GPU pool
+#ifdef HRL_BOUNDS
+#include <assert.h>
+#define HRL_CHECK(c) assert(c)
+#else
+#define HRL_CHECK(c) ((void)0)
+#endif
+
 struct V3 {
   float x, y, z;
 };
