@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B of the lane mappings: parity tests and bench for 4 / 8 / 16 lanes per env (HRL_B200_LANES)
-L=${1:-r2b}
+L=${1:-ablanes}
 mkdir -p gpurun_out
 for lanes in 4 8 16; do
   HRL_B200_LANES=$lanes timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/test_${L}_l$lanes.log 2>&1
