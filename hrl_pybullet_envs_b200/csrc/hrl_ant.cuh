@@ -77,6 +77,9 @@
 #ifndef HRL_DELASSUS
 #define HRL_DELASSUS 0
 #endif
+#ifndef HRL_LOOKAHEAD
+#define HRL_LOOKAHEAD 0
+#endif
 #define HRL_DS_MAXC 4        // contacts per env the fast path holds (more: velocity-space sweep)
 #define HRL_DS_P 24          // positions
 #define HRL_DS_ROWS 20       // rows of What: limit p -> p, contact c direction d -> 8 + 3 c + d
@@ -518,10 +521,19 @@ __device__ __forceinline__ void axpy14(float2 y[7], const float2 a[7], float s) 
 // Idle visits use an all-zero row (HRL_ROW_ZERO; a = 0, dinv = rhs = 0, impulse 0): dl = 0 falls out
 // of the arithmetic, no predicate needed.
 template <bool HAS_HI>
-__device__ __forceinline__ void single_visit(float* __restrict__ lp, float2 dv[7], const Row& R, float lam, float hi) {
+__device__ __forceinline__ float single_visit(float* __restrict__ lp, float2 dv[7], const Row& R, float lam, float hi) {
   // new impulse = clamp(lam + rhs' - (a . dv') / (a . a)): lam + rhs' is formed off the dependency chain, which is
   // dot -> fma -> max (-> min) -> sub -> axpy
   float nl = fmaxf(fmaf(-dot14(R.p, dv), R.dinv, lam + R.rhs), 0.f);
+  if (HAS_HI) nl = fminf(nl, hi);
+  *lp = nl;
+  axpy14(dv, R.p, nl - lam);
+  return nl - lam;
+}
+// The same visit with the row velocity a . dv' handed in (look-ahead, see the sweep): returns nothing, applies the delta.
+template <bool HAS_HI>
+__device__ __forceinline__ void single_visit_pre(float* __restrict__ lp, float2 dv[7], const Row& R, float lam, float hi, float d) {
+  float nl = fmaxf(fmaf(-d, R.dinv, lam + R.rhs), 0.f);
   if (HAS_HI) nl = fminf(nl, hi);
   *lp = nl;
   axpy14(dv, R.p, nl - lam);
@@ -1142,9 +1154,19 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
       int t = 0;
       for (; t + 1 < maxNL; t += 2) {
         r1 = HRL_LIM_ROW(t + 1); p1 = HRL_LIM_LAM(t + 1, r1); R1 = ld_row<COMPACT>(rb, r1); l1 = *p1;
+#if HRL_LOOKAHEAD
+        // look-ahead inside the trip: both rows are in registers, so the second visit's row velocity is taken against the
+        // velocity BEFORE the first visit (off the chain, next to it) and corrected with the rows' Gram entry:
+        // a1 . (dv + a0 dl0) = a1 . dv + (a0 . a1) dl0 - its dependent chain is fma -> fma -> max -> min -> sub
+        const float g01 = dot14(R0.p, R1.p), d1 = dot14(R1.p, dv);
+        const float dl0 = single_visit<true>(p0, dv, R0, l0, P.max_imp);
+        r0 = HRL_LIM_ROW(t + 2); p0 = HRL_LIM_LAM(t + 2, r0); R0 = ld_row<COMPACT>(rb, r0); l0 = *p0;
+        single_visit_pre<true>(p1, dv, R1, l1, P.max_imp, fmaf(g01, dl0, d1));
+#else
         single_visit<true>(p0, dv, R0, l0, P.max_imp);
         r0 = HRL_LIM_ROW(t + 2); p0 = HRL_LIM_LAM(t + 2, r0); R0 = ld_row<COMPACT>(rb, r0); l0 = *p0;
         single_visit<true>(p1, dv, R1, l1, P.max_imp);
+#endif
       }
       if (t < maxNL) single_visit<true>(p0, dv, R0, l0, P.max_imp);
     }
@@ -1157,9 +1179,16 @@ __device__ __forceinline__ void ant_substep(AntLane& s, const SubstepParams& P, 
         int t = 0;
         for (; t + 1 < maxNC; t += 2) {
           c1 = HRL_SLOT(t + 1); R1 = ld_row<COMPACT>(rb, HRL_ROW_NRM_LAST - c1); l1 = cl[c1].z;
+#if HRL_LOOKAHEAD
+          const float g01 = dot14(R0.p, R1.p), d1 = dot14(R1.p, dv);
+          const float dl0 = single_visit<false>(&cl[c0].z, dv, R0, l0, 0.f);
+          c0 = HRL_SLOT(t + 2); R0 = ld_row<COMPACT>(rb, HRL_ROW_NRM_LAST - c0); l0 = cl[c0].z;
+          single_visit_pre<false>(&cl[c1].z, dv, R1, l1, 0.f, fmaf(g01, dl0, d1));
+#else
           single_visit<false>(&cl[c0].z, dv, R0, l0, 0.f);
           c0 = HRL_SLOT(t + 2); R0 = ld_row<COMPACT>(rb, HRL_ROW_NRM_LAST - c0); l0 = cl[c0].z;
           single_visit<false>(&cl[c1].z, dv, R1, l1, 0.f);
+#endif
         }
         if (t < maxNC) single_visit<false>(&cl[c0].z, dv, R0, l0, 0.f);
       }
