@@ -468,17 +468,23 @@ __device__ __forceinline__ void emit_row(float4* __restrict__ rb, int pos, int k
 
 // ---- Blackwell packed fp32 (FFMA2 / FMUL2 / FADD2): two IEEE-rn fp32 operations per instruction ----
 #define HRL_U64(v) reinterpret_cast<unsigned long long&>(v)
+#ifndef HRL_SCALAR_FMA
+#define HRL_SCALAR_FMA 0   // 1: plain fp32 instructions instead of the packed ones (A/B only)
+#endif
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  if (HRL_SCALAR_FMA) return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
   float2 r;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(HRL_U64(r)) : "l"(HRL_U64(a)), "l"(HRL_U64(b)), "l"(HRL_U64(c)));
   return r;
 }
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  if (HRL_SCALAR_FMA) return make_float2(a.x * b.x, a.y * b.y);
   float2 r;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(HRL_U64(r)) : "l"(HRL_U64(a)), "l"(HRL_U64(b)));
   return r;
 }
 __device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  if (HRL_SCALAR_FMA) return make_float2(a.x + b.x, a.y + b.y);
   float2 r;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(HRL_U64(r)) : "l"(HRL_U64(a)), "l"(HRL_U64(b)));
   return r;
